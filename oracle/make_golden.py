@@ -1,0 +1,260 @@
+"""Golden-vector generator: runs the UNMODIFIED reference classes (``/root/reference/src/PaDT/models``) under
+``oracle/ref_shim.py`` on seeded tiny configs, checks ``oracle/padt_oracle.py`` against them bit-for-bit and
+writes the fixtures ``tests/golden/*.pt``.
+
+TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference):   python oracle/make_golden.py
+
+What is pinned by the reference itself (its own Python, verbatim): custom_visual_forward (padt.py:48-106),
+forward_main prefill + decode branches (padt.py:147-340) incl. prototype projection, extended embedding/logits and
+mask, vl_decode (padt.py:342-412), PaDTDecoder (padt_decoder.py), processor id shifts and the parser.
+What the shim has to supply because the pinned third-party versions are absent: FA2 attention
+numerics (restated in oracle.fa2_attention, used by both sides), flash-attn's apply_rotary_emb, and the
+transformers-4.50.0 ``get_rope_index`` (restated; KAT in tests/test_rope_index.py).  The greedy loop restates
+padt.py:671-757 because the copied HF-4.50 ``generate`` cannot run on transformers 5.5.0.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_shim  # noqa: E402
+import padt_oracle as O  # noqa: E402
+from padt_b200.config import padt_tiny  # noqa: E402
+from padt_b200.weights import random_weights  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _eager_fa2(module, query, key, value, attention_mask, scaling, dropout=0.0, **kwargs):
+    """Replacement for HF `eager_attention_forward` (HF:182-204) with FA2 numerics."""
+    B = query.shape[0]
+    outs = []
+    for b in range(B):
+        mask = None
+        if attention_mask is not None:
+            mask = attention_mask[b, 0] > -1.0
+        outs.append(O.fa2_attention(query[b], key[b], value[b], scaling, mask))
+    out = torch.stack(outs, 0).transpose(1, 2).contiguous()
+    return out, None
+
+
+def build_reference(cfg, weights):
+    padt, dec, proc = ref_shim.install()
+    import transformers.models.qwen2_5_vl.modeling_qwen2_5_vl as hf
+    from transformers import Qwen2_5_VLConfig
+    hf.eager_attention_forward = _eager_fa2
+    t, v, d = cfg.text, cfg.vision, cfg.decoder
+    hc = Qwen2_5_VLConfig(
+        text_config=dict(vocab_size=t.vocab_size, hidden_size=t.hidden_size, intermediate_size=t.intermediate_size,
+                         num_hidden_layers=t.num_layers, num_attention_heads=t.num_heads,
+                         num_key_value_heads=t.num_kv_heads, rms_norm_eps=t.rms_norm_eps,
+                         rope_parameters=dict(rope_type="default", rope_theta=t.rope_theta,
+                                              mrope_section=list(t.mrope_section)),
+                         tie_word_embeddings=t.tie_word_embeddings, use_sliding_window=False,
+                         max_position_embeddings=4096, pad_token_id=None),
+        vision_config=dict(depth=v.depth, hidden_size=v.hidden_size, intermediate_size=v.intermediate_size,
+                           num_heads=v.num_heads, out_hidden_size=v.out_hidden_size,
+                           fullatt_block_indexes=list(v.fullatt_block_indexes), window_size=v.window_size,
+                           patch_size=v.patch_size, spatial_merge_size=v.spatial_merge_size,
+                           temporal_patch_size=v.temporal_patch_size),
+        image_token_id=cfg.image_token_id, video_token_id=cfg.video_token_id,
+        vision_start_token_id=cfg.vision_start_token_id, vision_end_token_id=cfg.vision_end_token_id,
+        tie_word_embeddings=t.tie_word_embeddings,
+    )
+    hc.hidden_size = t.hidden_size
+    hc.vocab_size = t.vocab_size
+    hc.vl_decoder = dict(name="PaDTDecoder", attn_implementation="flash_attention_2", hidden_size=d.hidden_size,
+                         intermediate_size=d.intermediate_size, llm_hidden_state=t.hidden_size,
+                         num_heads=d.num_heads, spatial_merge_size=v.spatial_merge_size, use_mask_loss=True)
+    hc.use_visual_prototype_projection = cfg.use_visual_prototype_projection
+    hc._attn_implementation = "eager"
+    hc.text_config._attn_implementation = "eager"
+    hc.vision_config._attn_implementation = "eager"
+    # like from_pretrained(torch_dtype=bf16): instantiate under a bf16 default dtype so parameters are bf16 while
+    # the explicitly-fp32 rotary inv_freq buffers stay fp32 (a later .to(bf16) would round them)
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        model = padt.PaDTForConditionalGeneration(hc).eval()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    model.vl_decoder.dtype = torch.bfloat16
+    assert model.model.visual.rotary_pos_emb.inv_freq.dtype == torch.float32
+    assert model.model.language_model.rotary_emb.inv_freq.dtype == torch.float32
+    # 4.50 attribute layout expected by padt.py
+    model.__dict__["visual"] = model.model.visual
+    model.model.embed_tokens = model.model.language_model.embed_tokens
+    model.rope_deltas = None
+    model.get_rope_index = lambda input_ids=None, image_grid_thw=None, video_grid_thw=None, second_per_grid_ts=None, attention_mask=None: \
+        O.get_rope_index(cfg, input_ids, image_grid_thw, attention_mask)
+    sd = {}
+    for k, val in weights.items():
+        if k.startswith("visual."):
+            nk = "model." + k
+        elif k.startswith("model."):
+            nk = "model.language_model." + k[len("model."):]
+        else:
+            nk = k
+        sd[nk] = val
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    missing = [m for m in missing if "inv_freq" not in m and m != "model.embed_tokens.weight"  # alias of language_model.embed_tokens
+               and not (t.tie_word_embeddings and m == "lm_head.weight")]
+    assert not missing and not unexpected, (missing, unexpected)
+    if t.tie_word_embeddings:
+        model.lm_head.weight = model.model.language_model.embed_tokens.weight
+    return model, proc
+
+
+def ref_greedy(model, cfg, input_ids, attention_mask, pixel_values, grid, steps, forced=None):
+    """padt.py:671-757 restated around the reference's own forward_main (eos disabled -> fixed length)."""
+    from transformers import DynamicCache
+    B, L = input_ids.shape
+    cache = DynamicCache(config=model.config)
+    model.rope_deltas = None
+    out = model.forward_main(input_ids=input_ids, attention_mask=attention_mask, pixel_values=pixel_values,
+                             image_grid_thw=grid, past_key_values=cache, use_cache=True, output_hidden_states=True,
+                             return_dict=True, cache_position=torch.arange(L))
+    past = dict(past_image_embeds=out.past_image_embeds, past_logit_mask=out.past_logit_mask,
+                past_high_res_image_embeds=out.past_high_res_image_embeds, past_visual_pe=out.past_visual_pe)
+    seq, mask = input_ids.clone(), attention_mask.clone()
+    hid, logit_steps, arg_steps = [out.hidden_states[-1]], [], []
+    for s in range(steps):
+        scores = out.logits[:, -1, :].clone().float()
+        logit_steps.append(scores)
+        nxt = torch.argmax(scores, dim=-1)
+        arg_steps.append(nxt.clone())
+        if forced is not None:
+            nxt = forced[:, s].clone()
+        seq = torch.cat([seq, nxt[:, None]], dim=-1)
+        if s == steps - 1:
+            break
+        mask = torch.cat([mask, torch.ones(B, 1, dtype=mask.dtype)], dim=-1)
+        out = model.forward_main(input_ids=nxt[:, None], attention_mask=mask, past_key_values=cache, use_cache=True,
+                                 output_hidden_states=True, return_dict=True,
+                                 cache_position=torch.tensor([L + s]), **past)
+        hid.append(out.hidden_states[-1])
+    return dict(sequences=seq, hidden_steps=hid, logits_steps=logit_steps, argmax_steps=arg_steps, **past)
+
+
+def make_inputs(cfg, grids, prompt_lens, seed):
+    """Chat-template-shaped rows: text, <vision_start>, M x <image_pad>, <vision_end>, text; left padded."""
+    g = torch.Generator().manual_seed(seed)
+    V = cfg.text.vocab_size
+    rows = []
+    for (t, h, w), pl in zip(grids, prompt_lens):
+        M = t * h * w // 4
+        pre = torch.randint(0, V - 16, (3,), generator=g).tolist()
+        post = torch.randint(0, V - 16, (pl,), generator=g).tolist()
+        rows.append(pre + [cfg.vision_start_token_id] + [cfg.image_token_id] * M + [cfg.vision_end_token_id] + post)
+    L = max(len(r) for r in rows)
+    ids = torch.full((len(rows), L), cfg.pad_token_id, dtype=torch.long)
+    mask = torch.zeros((len(rows), L), dtype=torch.long)
+    for i, r in enumerate(rows):
+        ids[i, L - len(r):] = torch.tensor(r)
+        mask[i, L - len(r):] = 1
+    P = sum(t * h * w for t, h, w in grids)
+    pixel_values = torch.randn((P, cfg.vision.patch_dim), generator=g).to(torch.bfloat16)
+    grid = torch.tensor(grids, dtype=torch.long)
+    return ids, mask, pixel_values, grid
+
+
+def eq(a, b, what):
+    if isinstance(a, (tuple, list)):
+        assert len(a) == len(b), what
+        for i, (x, y) in enumerate(zip(a, b)):
+            eq(x, y, f"{what}[{i}]")
+        return
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    same = torch.equal(a, b) if a.dtype != torch.float32 and a.dtype != torch.bfloat16 else \
+        bool(((a == b) | (torch.isinf(a) & torch.isinf(b))).all())
+    if not same:
+        d = (a.float() - b.float()).abs()
+        d = d[torch.isfinite(d)]
+        raise AssertionError(f"oracle != reference for {what}: max abs diff {float(d.max())}")
+
+
+def case(name, cfg, wseed, grids, prompt_lens, steps, iseed, objects):
+    w = random_weights(cfg, seed=wseed)
+    model, proc = build_reference(cfg, w)
+    ids, mask, pv, grid = make_inputs(cfg, grids, prompt_lens, iseed)
+    V = cfg.text.vocab_size
+    with torch.no_grad():
+        # ---- ViT alone (V1-V6)
+        r_emb, r_high, r_pe = model.visual(pv, grid_thw=grid)
+        o_emb, o_high, o_pe = O.vit_forward(w, cfg, pv, grid)
+        eq(o_emb, r_emb, "image_embeds"); eq(o_high, r_high, "high_res"); eq(o_pe[0], r_pe[0], "cos"); eq(o_pe[1], r_pe[1], "sin")
+        # ---- free-running greedy (E1-E4, R1, T1, T2, S1)
+        rg = ref_greedy(model, cfg, ids, mask, pv, grid, steps)
+        og = O.greedy_generate(w, cfg, ids, mask, pv, grid, steps, eos_token_ids=[])
+        eq(og["sequences"], rg["sequences"], "sequences")
+        valid = mask.bool()
+        eq(og["hidden_steps"][0][valid], rg["hidden_steps"][0][valid], "prefill hidden (non-pad rows)")
+        for s in range(1, len(rg["hidden_steps"])):
+            eq(og["hidden_steps"][s], rg["hidden_steps"][s], f"hidden step {s}")
+        for s in range(steps):
+            eq(og["logits_steps"][s], rg["logits_steps"][s], f"logits step {s}")
+        eq(og["past_image_embeds"], rg["past_image_embeds"], "prototypes")
+        eq(og["past_logit_mask"], rg["past_logit_mask"], "logit mask")
+        # ---- teacher-forced run that feeds VRT ids back in (exercises ext[input_ids] for ids >= V)
+        off = O.patch_offsets(cfg, grid)
+        g = torch.Generator().manual_seed(iseed + 7)
+        forced = torch.randint(0, V - 16, (len(grids), steps), generator=g)
+        for b in range(len(grids)):
+            Mb = off[b + 1] - off[b]
+            pos = torch.randperm(steps, generator=g)[: steps // 2]
+            forced[b, pos] = V + off[b] + torch.randint(0, Mb, (len(pos),), generator=g)
+        rf = ref_greedy(model, cfg, ids, mask, pv, grid, steps, forced=forced)
+        of = O.greedy_generate(w, cfg, ids, mask, pv, grid, steps, eos_token_ids=[], forced_tokens=forced)
+        eq(of["sequences"], rf["sequences"], "forced sequences")
+        eq(torch.stack(of["argmax_steps"]), torch.stack(rf["argmax_steps"]), "forced argmax")
+        for s in range(1, len(rf["hidden_steps"])):
+            eq(of["hidden_steps"][s], rf["hidden_steps"][s], f"forced hidden step {s}")
+        # ---- vl_decode (D1-D4): VRT features = final-norm hidden of the step that predicted each VRT
+        feats = []
+        for b, objs in enumerate(objects):
+            sample = []
+            for (s0, n) in objs:
+                sample.append(torch.cat([rf["hidden_steps"][s][b] for s in range(s0, s0 + n)], dim=0))
+            feats.append(sample)
+        rd = model.vl_decode(feats, rf["past_image_embeds"], rf["past_high_res_image_embeds"], grid, rf["past_visual_pe"])
+        od = O.vl_decode(w, cfg, feats, of["past_image_embeds"], of["past_high_res_image_embeds"], grid, of["past_visual_pe"])
+        for k in ("pred_boxes", "pred_score", "pred_mask"):
+            eq(od[k], rd[k], k)
+        eq(od["pred_mask_valid_hw"][0], rd["pred_mask_valid_hw"][0], "Hs"); eq(od["pred_mask_valid_hw"][1], rd["pred_mask_valid_hw"][1], "Ws")
+        assert od["sample_idx"] == rd["sample_idx"]
+    top = [torch.topk(l, 8, dim=-1) for l in rg["logits_steps"]]
+    fx = dict(
+        name=name, cfg_name=cfg.name, tie=cfg.text.tie_word_embeddings, vocab=V, wseed=wseed,
+        input_ids=ids, attention_mask=mask, pixel_values=pv, grid=grid, steps=steps,
+        image_embeds=r_emb, high_res=r_high, cos=r_pe[0], sin=r_pe[1],
+        prototypes=rg["past_image_embeds"], sequences=rg["sequences"],
+        last_hidden=torch.stack([h[:, -1, :] for h in rg["hidden_steps"]]),
+        top8_values=torch.stack([t.values for t in top]), top8_indices=torch.stack([t.indices for t in top]),
+        forced=forced, forced_argmax=torch.stack(rf["argmax_steps"]),
+        forced_last_hidden=torch.stack([h[:, -1, :] for h in rf["hidden_steps"]]),
+        forced_top2=torch.stack([torch.topk(l, 2, dim=-1).values for l in rf["logits_steps"]]),
+        objects=objects, pred_boxes=rd["pred_boxes"], pred_score=rd["pred_score"], pred_mask=rd["pred_mask"],
+        Hs=rd["pred_mask_valid_hw"][0], Ws=rd["pred_mask_valid_hw"][1], sample_idx=rd["sample_idx"],
+    )
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fx, path)
+    print(f"[golden] {name}: oracle == reference (bit-exact); wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB); "
+          f"sequence tail {rg['sequences'][0, -steps:].tolist()}")
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    # B=1, tied head, ragged windows (grid 8x12 -> merged 4x6: windows of 16 and 8 merged units)
+    case("tiny_b1", padt_tiny(tie=True), 0, [(1, 8, 12)], [9], 12, 1, [[(2, 3), (7, 2)]])
+    # B=2, left padded, two different grids, untied head
+    case("tiny_b2", padt_tiny(tie=False), 1, [(1, 8, 12), (1, 4, 8)], [5, 11], 10, 2, [[(1, 2)], [(3, 1), (5, 3)]])
+
+
+if __name__ == "__main__":
+    main()
