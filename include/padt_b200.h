@@ -1,0 +1,117 @@
+/* padt_b200 -- C ABI of the B200-native PaDT generate/decode hot path.
+ *
+ * The reference (Gorilla-Lab-SCUT/PaDT) has no FFI of its own: its boundary is three Python names
+ * (src/PaDT/__init__.py:1).  This library is what those names call into in padt_b200/ (ctypes binding in
+ * padt_b200/_capi.py); each entry point below cites the reference code it replaces.  INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions: all data pointers are BORROWED device pointers (torch-owned storage) unless a name ends in _host;
+ * activations/weights are bf16, positional tables fp32, ids int64; every call takes a cudaStream_t, returns 0 on
+ * success or <0 (message via padt_last_error()); one handle per (process, GPU); a handle is not thread-safe.
+ */
+#ifndef PADT_B200_H
+#define PADT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct PadtHandle PadtHandle;
+typedef void* padt_stream_t; /* cudaStream_t */
+
+/* Model dimensions == padt_b200.config.PadtConfig (Qwen2.5-VL config.json + the `vl_decoder` dict of
+ * src/PaDT/trainer/padt_sft_trainer.py:151-160 as fixed up at src/PaDT/models/padt.py:127-130). */
+typedef struct PadtDims {
+    int32_t vit_depth, vit_hidden, vit_inter, vit_heads, vit_in_ch, vit_patch, vit_tpatch, vit_merge, vit_window, vit_out_hidden;
+    int32_t vit_n_fullatt;
+    int32_t vit_fullatt[8];
+    int32_t D, I, n_layers, n_heads, n_kv_heads, vocab;
+    float rms_eps;
+    int32_t mrope0, mrope1, mrope2;
+    int32_t tie_word_embeddings;
+    int32_t dec_hidden, dec_inter, dec_heads;
+    int32_t use_proto_proj, lora_r;
+} PadtDims;
+
+const char* padt_last_error(void);
+const char* padt_version(void);
+/* Number of CUDA kernels this library has launched in this process (graph replays count their kernel nodes). */
+unsigned long long padt_launch_count(void);
+
+/* Canonical weight order (== padt_b200.weights.weight_shapes(cfg), HF-4.50 key layout of the reference checkpoints). */
+int padt_weight_count(const PadtDims* dims);
+const char* padt_weight_name(const PadtDims* dims, int index);
+
+/* Create an engine.  `weights[i]` = device pointer of tensor padt_weight_name(dims, i) (bf16, contiguous).
+ * `llm_cos`/`llm_sin`: bf16 [max_pos, head_dim/2] rotary tables (HF:595-608 evaluated on the host).
+ * Replaces PaDTForConditionalGeneration.__init__/from_pretrained module construction (padt.py:115-132): the engine
+ * packs fused/interleaved copies of the projection weights it streams (q|k|v rows, gate/up interleaved). */
+int padt_create(const PadtDims* dims, const void* const* weights, int n_weights, const void* llm_cos, const void* llm_sin,
+                int max_pos, PadtHandle** out);
+int padt_destroy(PadtHandle* h);
+
+/* V1-V6: custom_visual_forward (padt.py:48-106).  pixel_values [P,1176]; grid_thw_host [n_img*3];
+ * pos_cos/pos_sin: fp32 DEVICE tables [tab_rows, head_dim/4] = cos/sin(outer(arange, inv_freq)) (HF:117-130).
+ * Outputs: image_embeds [P/4, D] (raster-merged order), high_res [P, vit_hidden] (window order), cos/sin fp32
+ * [P, head_dim] (window order). */
+int padt_vit_forward(PadtHandle* h, const void* pixel_values, const int64_t* grid_thw_host, int n_img, const float* pos_cos,
+                     const float* pos_sin, int tab_rows, void* image_embeds, void* high_res, float* cos, float* sin,
+                     padt_stream_t stream);
+
+/* E1: prototype projection (padt.py:187-191). */
+int padt_prototypes(PadtHandle* h, const void* image_embeds, int n_rows, void* prototypes, padt_stream_t stream);
+
+/* Generation-time buffers the caller owns (all device). */
+typedef struct PadtGenBuffers {
+    int64_t* tokens_out;    /* [max_steps,B] tokens appended to the sequences (padt.py:749-752) */
+    int64_t* argmax_out;    /* [max_steps,B] raw arg-max per step, may be NULL */
+    void* hidden_steps;     /* [max_steps,B,D] final-norm state that predicted token k (padt.py:732-737), may be NULL */
+    void* last_hidden;      /* [B,D] */
+    void* prefill_hidden;   /* [B,L,D] final-norm states of the prompt (hidden_states[0][-1]), may be NULL */
+    const int64_t* forced;  /* [max_steps,B] teacher-forced feedback tokens, may be NULL */
+    int32_t max_steps;
+} PadtGenBuffers;
+
+/* E2-E4, R1, T1, T2 (prefill): forward_main pixel_values branch after the ViT (padt.py:193-219,256-301).
+ * input_ids [B,L] int64 (global VRT ids); image_slot [B,L] int32 (k-th <|image_pad|> -> k, else -1: the masked_scatter
+ * order of padt.py:219); pos3 [3,B,L] int32 = get_rope_index (transformers 4.50 semantics); *_host arrays have B
+ * entries: kv_start = number of left pads, rope_delta (padt.py:266), vrt_lo/hi = prototype-row range the row may emit
+ * (padt.py:196-201).  Leaves the arg-max partials of the last position in the handle; call padt_decode next. */
+int padt_prefill(PadtHandle* h, const int64_t* input_ids, const int32_t* image_slot, const int32_t* pos3,
+                 const int32_t* kv_start_host, const int32_t* rope_delta_host, const int32_t* vrt_lo_host, const int32_t* vrt_hi_host,
+                 const void* image_embeds, const void* prototypes, int n_protos, int B, int L,
+                 const int64_t* eos_ids_host, int n_eos, int64_t pad_id, const PadtGenBuffers* bufs, padt_stream_t stream);
+
+/* S1 + T1/T2 (decode): n_steps iterations of {sample token t, embed it, run the layers, logits} with no host sync
+ * (padt.py:671-757 minus the Python loop), then one trailing sample if `finish` != 0. */
+int padt_decode(PadtHandle* h, int n_steps, int finish, padt_stream_t stream);
+/* Synchronises the stream and reads {tokens sampled so far, rows still unfinished}. */
+int padt_decode_status(PadtHandle* h, int32_t* n_sampled, int32_t* n_unfinished, padt_stream_t stream);
+/* Selects the decode-step implementation: 0 = per-layer kernels under one CUDA graph, 1 = same without graph. */
+int padt_set_option(PadtHandle* h, const char* name, int value);
+
+/* D1-D4: vl_decode + PaDTDecoder.forward (padt.py:342-412, padt_decoder.py:187-276).
+ * vrt_feats [sum n_vrt, D]; obj_vrt_count_host / obj_sample_host [n_obj]; low [sum M, D]; high [sum P, vit_hidden];
+ * cos/sin fp32 [sum P, head_dim]; grid_thw_host [n_img*3].  Outputs: boxes [n_obj,4] (sigmoid applied), scores [n_obj,1]
+ * (logits), masks [n_obj, 4*hmax, 4*wmax] (logits, zero outside each object's valid region). */
+int padt_vl_decode(PadtHandle* h, const void* vrt_feats, const int32_t* obj_vrt_count_host, const int32_t* obj_sample_host, int n_obj,
+                   const void* low, const void* high, const float* cos, const float* sin, const int64_t* grid_thw_host, int n_img,
+                   void* boxes, void* scores, void* masks, int hmax, int wmax, padt_stream_t stream);
+
+/* Kernel-level entry points used by the parity tests (tests/test_ops_gpu.py). */
+int padt_op_gemm(int epilogue, const void* A, int lda, const void* W, int ldw, const void* bias, const void* resid, int ldr, void* C,
+                 int ldc, const int32_t* out_row_map, int M, int N, int K, padt_stream_t stream);
+int padt_op_rmsnorm(const void* x, const void* w, void* y, int rows, int dim, float eps, padt_stream_t stream);
+int padt_op_attention(const void* q, const void* k, const void* v, void* o, int64_t q_row, int64_t q_head, int64_t k_row, int64_t k_head,
+                      int64_t v_row, int64_t v_head, int64_t o_row, int64_t o_head, const int32_t* q_off, const int32_t* q_len,
+                      const int32_t* k_off, const int32_t* k_len, const int32_t* k_start, int n_seg, int n_heads, int group,
+                      int max_q_len, int head_dim, int causal, float scale, padt_stream_t stream);
+int padt_op_rope_neox(void* x, int64_t row_stride, int n_heads, int head_dim, const float* cos, const float* sin, int cs_ld, int rows,
+                      padt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PADT_B200_H */

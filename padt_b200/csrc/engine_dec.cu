@@ -1,0 +1,197 @@
+// vl_decode + PaDT decoder (host orchestration).
+// Reference: vl_decode padt.py:342-412; PaDTDecoder.forward padt_decoder.py:187-276; PaDTDecoderBlock.forward :95-128;
+// PaDTDecoderFlashAttention2.forward :20-60.  Quirks kept on purpose: high-res features and the
+// rotary table stay in ViT window order while low-res features are raster order; the mask scatter treats the
+// high-res index as raster; query_pos is the initial query tensor itself.
+// Object-independent work is de-duplicated where the result is bit-identical: input_projection of the low-res
+// features runs once per image instead of once per object (padt.py:370 replicates, padt_decoder.py:210 re-projects).
+#include "engine.h"
+
+namespace {
+
+struct Scratch {
+    bf16 *a, *b, *c, *d;   // memory-sized [NM, H]
+    bf16 *qa, *qb, *qc, *qd, *qe;  // query-sized [NQ, max(H, Ipad)]
+};
+
+struct Segs {   // device int arrays per object
+    const int *q_off, *q_len, *m_off, *m_len;
+    int n_obj, max_q, max_m;
+};
+
+int dec_attention(PadtHandle* h, const DecAttnW& w, const bf16* q_in, int nq_rows, const bf16* k_in, const bf16* v_in, int nk_rows,
+                  const int* q_off, const int* q_len, int max_q, const int* k_off, const int* k_len, int n_seg,
+                  bool rope_q, bool rope_k, const float* cos, const float* sin, const int* pe_map,
+                  bf16* qbuf, bf16* kbuf, bf16* vbuf, bf16* obuf, const bf16* resid, bf16* out, cudaStream_t st) {
+    const int H = h->d.dec_hidden, nh = h->d.dec_heads, hd = h->dec_hd;
+    RC(gemm(EPI_NONE, q_in, H, w.wq, H, w.bq, nullptr, 0, qbuf, H, nullptr, nq_rows, H, H, st));
+    RC(gemm(EPI_NONE, k_in, H, w.wk, H, w.bk, nullptr, 0, kbuf, H, nullptr, nk_rows, H, H, st));
+    RC(gemm(EPI_NONE, v_in, H, w.wv, H, w.bv, nullptr, 0, vbuf, H, nullptr, nk_rows, H, H, st));
+    if (rope_q) RC(launch_rope_neox_f32(qbuf, H, nh, hd, cos, sin, hd, pe_map, nq_rows, st));
+    if (rope_k) RC(launch_rope_neox_f32(kbuf, H, nh, hd, cos, sin, hd, pe_map, nk_rows, st));
+    AttnParams a = {};
+    a.q = qbuf; a.k = kbuf; a.v = vbuf; a.o = obuf;
+    a.q_row = a.k_row = a.v_row = a.o_row = H; a.q_head = a.k_head = a.v_head = a.o_head = hd;
+    a.q_off = q_off; a.q_len = q_len; a.k_off = k_off; a.k_len = k_len; a.k_start = nullptr;
+    a.n_seg = n_seg; a.n_heads = nh; a.group = 1; a.max_q_len = max_q; a.head_dim = hd; a.causal = 0;
+    a.scale = 1.0f / sqrtf((float)hd);   // flash_attn default softmax_scale (padt_decoder.py:55)
+    RC(launch_attention(a, st));
+    RC(gemm(EPI_RESID, obuf, H, w.wp, H, w.bp, resid, H, out, H, nullptr, nq_rows, H, H, st));
+    return 0;
+}
+
+// One PaDTDecoderBlock (padt_decoder.py:95-128), query and memory updated in place.
+int dec_block(PadtHandle* h, const DecBlockW& w, bf16* query, int NQ, bf16* memory, int NM, const bf16* query_pos, const Segs& sg,
+              const float* cos, const float* sin, const int* pe_map, const Scratch& s, cudaStream_t st) {
+    const int H = h->d.dec_hidden, Ip = h->dec_ipad, Id = h->d.dec_inter;
+    const float eps = 1e-6f;
+    // self attention: q,k from (norm1(query)+pos), v from norm1(query)                         (:112-113)
+    RC(launch_rmsnorm(query, H, w.norm[0], s.qa, H, NQ, H, eps, st));
+    RC(launch_add(s.qa, query_pos, s.qb, (long long)NQ * H, st));
+    RC(dec_attention(h, w.self_attn, s.qb, NQ, s.qb, s.qa, NQ, sg.q_off, sg.q_len, sg.max_q, sg.q_off, sg.q_len, sg.n_obj, false, false,
+                     cos, sin, nullptr, s.qc, s.qd, s.qe, s.qb, query, query, st));
+    // query -> image cross attention: q from norm2(query)+pos, k = rope(k_proj(norm3(mem))), v = v_proj(norm3(mem))   (:116-118)
+    RC(launch_rmsnorm(query, H, w.norm[1], s.qa, H, NQ, H, eps, st));
+    RC(launch_add(s.qa, query_pos, s.qb, (long long)NQ * H, st));
+    RC(launch_rmsnorm(memory, H, w.norm[2], s.a, H, NM, H, eps, st));
+    RC(dec_attention(h, w.q2i, s.qb, NQ, s.a, s.a, NM, sg.q_off, sg.q_len, sg.max_q, sg.m_off, sg.m_len, sg.n_obj, false, true, cos, sin,
+                     pe_map, s.qc, s.b, s.c, s.qd, query, query, st));
+    // query MLP                                                                                  (:121)
+    RC(launch_rmsnorm(query, H, w.norm[3], s.qa, H, NQ, H, eps, st));
+    RC(gemm(EPI_GELU, s.qa, H, w.w0, H, w.b0, nullptr, 0, s.qe, Ip, nullptr, NQ, Id, H, st));
+    RC(gemm(EPI_RESID, s.qe, Ip, w.w2, Ip, w.b2, query, H, query, H, nullptr, NQ, H, Id, st));
+    // image -> query cross attention (memory update): q = rope(q_proj(norm6(mem))), k from norm5(query)+pos, v from norm5(query)  (:124-126)
+    RC(launch_rmsnorm(query, H, w.norm[4], s.qa, H, NQ, H, eps, st));
+    RC(launch_add(s.qa, query_pos, s.qb, (long long)NQ * H, st));
+    RC(launch_rmsnorm(memory, H, w.norm[5], s.a, H, NM, H, eps, st));
+    RC(dec_attention(h, w.i2q, s.a, NM, s.qb, s.qa, NQ, sg.m_off, sg.m_len, sg.max_m, sg.q_off, sg.q_len, sg.n_obj, true, false, cos, sin,
+                     pe_map, s.b, s.qc, s.qd, s.c, memory, memory, st));
+    return 0;
+}
+
+int input_projection(PadtHandle* h, const bf16* x, int rows, bf16* tmp_n, bf16* tmp_h, bf16* out, cudaStream_t st) {
+    // RMSNorm(D) -> Linear(D,H) -> GELU -> Linear(H,H)     (padt_decoder.py:142-147)
+    const int D = h->d.D, H = h->d.dec_hidden;
+    RC(launch_rmsnorm(x, D, h->ip_ln, tmp_n, D, rows, D, 1e-6f, st));
+    RC(gemm(EPI_GELU, tmp_n, D, h->ip_w1, D, h->ip_b1, nullptr, 0, tmp_h, H, nullptr, rows, H, D, st));
+    RC(gemm(EPI_NONE, tmp_h, H, h->ip_w3, H, h->ip_b3, nullptr, 0, out, H, nullptr, rows, H, H, st));
+    return 0;
+}
+
+int mlp3(PadtHandle* h, const Mlp3W& m, const bf16* x, int rows, int out_dim, bf16* t0, bf16* t1, bf16* out, cudaStream_t st) {
+    const int H = h->d.dec_hidden;
+    RC(gemm(EPI_GELU, x, H, m.w0, H, m.b0, nullptr, 0, t0, H, nullptr, rows, H, H, st));
+    RC(gemm(EPI_GELU, t0, H, m.w2, H, m.b2, nullptr, 0, t1, H, nullptr, rows, H, H, st));
+    RC(gemm(EPI_NONE, t1, H, m.w4, H, m.b4, nullptr, 0, out, out_dim, nullptr, rows, out_dim, H, st));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int padt_vl_decode(PadtHandle* h, const void* vrt_feats, const int32_t* obj_vrt_count_host, const int32_t* obj_sample_host, int n_obj,
+                              const void* low, const void* high, const float* cos, const float* sin, const int64_t* grid_thw_host, int n_img,
+                              void* boxes, void* scores, void* masks, int hmax, int wmax, padt_stream_t stream) {
+    PADT_REQUIRE(h && vrt_feats && obj_vrt_count_host && obj_sample_host && low && high && cos && sin && grid_thw_host && boxes && scores,
+                 "null argument");
+    PADT_REQUIRE(n_obj >= 1, "vl_decode needs at least one object (the empty case is handled by the caller, padt.py:405-412)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const PadtDims& d = h->d;
+    const int H = d.dec_hidden, D = d.D, Ip = h->dec_ipad, hd = h->dec_hd, unit = d.vit_merge * d.vit_merge;
+    // ---- host index tables
+    std::vector<int> p_off(n_img + 1, 0), P(n_img), Wimg(n_img), Himg(n_img);
+    for (int i = 0; i < n_img; ++i) {
+        P[i] = (int)(grid_thw_host[i * 3] * grid_thw_host[i * 3 + 1] * grid_thw_host[i * 3 + 2]);
+        Himg[i] = (int)grid_thw_host[i * 3 + 1]; Wimg[i] = (int)grid_thw_host[i * 3 + 2];
+        p_off[i + 1] = p_off[i] + P[i];
+    }
+    int n_vrt = 0, NQ = 0, NL = 0, NH = 0, max_q = 0, max_l = 0, max_h = 0;
+    std::vector<int> q_off(n_obj), q_len(n_obj), l_off(n_obj), l_len(n_obj), h_off(n_obj), h_len(n_obj), cu_patch(n_obj + 1, 0), obj_w(n_obj);
+    std::vector<int> q_src, tok_rows(3 * n_obj);
+    for (int o = 0; o < n_obj; ++o) {
+        int s = obj_sample_host[o], nv = obj_vrt_count_host[o];
+        PADT_REQUIRE(s >= 0 && s < n_img && nv >= 1, "object table");
+        PADT_REQUIRE(Himg[s] <= hmax && Wimg[s] <= wmax, "mask canvas smaller than an object's grid");
+        q_off[o] = NQ; q_len[o] = 3 + nv;
+        for (int k = 0; k < 3; ++k) { q_src.push_back(-(k + 1)); tok_rows[k * n_obj + o] = NQ + k; }
+        for (int k = 0; k < nv; ++k) q_src.push_back(n_vrt + k);
+        n_vrt += nv; NQ += 3 + nv;
+        l_off[o] = NL; l_len[o] = P[s] / unit; NL += P[s] / unit;
+        h_off[o] = NH; h_len[o] = P[s]; NH += P[s];
+        cu_patch[o + 1] = NH; obj_w[o] = Wimg[s];
+        max_q = q_len[o] > max_q ? q_len[o] : max_q;
+        max_l = l_len[o] > max_l ? l_len[o] : max_l;
+        max_h = h_len[o] > max_h ? h_len[o] : max_h;
+    }
+    // row maps: replicated low-res rows -> per-image projected rows; pe rows (low: first patch of each 4-group, :212)
+    std::vector<int> low_src(NL), low_pe(NL), high_src(NH);
+    for (int o = 0; o < n_obj; ++o) {
+        int s = obj_sample_host[o];
+        for (int m = 0; m < l_len[o]; ++m) { low_src[l_off[o] + m] = p_off[s] / unit + m; low_pe[l_off[o] + m] = p_off[s] + m * unit; }
+        for (int p = 0; p < h_len[o]; ++p) high_src[h_off[o] + p] = p_off[s] + p;
+    }
+    std::vector<int> packed;
+    auto put = [&](const std::vector<int>& v) { size_t off = packed.size(); packed.insert(packed.end(), v.begin(), v.end()); while (packed.size() % 4) packed.push_back(0); return off; };
+    size_t i_qoff = put(q_off), i_qlen = put(q_len), i_loff = put(l_off), i_llen = put(l_len), i_hoff = put(h_off), i_hlen = put(h_len);
+    size_t i_cup = put(cu_patch), i_objw = put(obj_w), i_qsrc = put(q_src), i_tok = put(tok_rows), i_lsrc = put(low_src), i_lpe = put(low_pe),
+           i_hsrc = put(high_src);
+    RC(h->dec_ints.ensure(packed.size() * sizeof(int)));
+    PADT_CHECK_CUDA(cudaMemcpyAsync(h->dec_ints.p, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    PADT_CHECK_CUDA(cudaStreamSynchronize(st));
+    const int* I = h->dec_ints.as<int>();
+    // ---- workspace
+    const int M_all = p_off[n_img] / unit;
+    const int qw = H > Ip ? H : Ip;
+    const int rows_ip = n_vrt > M_all ? n_vrt : M_all;
+    size_t off = 0;
+    auto take = [&](size_t elems) { size_t o = off; off = (off + elems * 2 + 255) / 256 * 256; return o; };
+    size_t o_ipn = take((size_t)rows_ip * D), o_iph = take((size_t)rows_ip * H), o_vp = take((size_t)n_vrt * H), o_lowimg = take((size_t)M_all * H);
+    size_t o_query = take((size_t)NQ * H), o_qpos = take((size_t)NQ * H);
+    size_t o_q[5];
+    for (int k = 0; k < 5; ++k) o_q[k] = take((size_t)NQ * qw);
+    size_t o_lowmem = take((size_t)NL * H), o_highmem = take((size_t)NH * H);
+    size_t o_m[4];
+    for (int k = 0; k < 4; ++k) o_m[k] = take((size_t)NH * H);
+    size_t o_tok = take((size_t)3 * n_obj * H), o_t0 = take((size_t)n_obj * H), o_t1 = take((size_t)n_obj * H), o_hyper = take((size_t)n_obj * (H / 16));
+    RC(h->dec_dws.ensure(off));
+    uint8_t* base = h->dec_dws.as<uint8_t>();
+    auto at = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
+    Scratch sc;
+    sc.a = at(o_m[0]); sc.b = at(o_m[1]); sc.c = at(o_m[2]); sc.d = at(o_m[3]);
+    sc.qa = at(o_q[0]); sc.qb = at(o_q[1]); sc.qc = at(o_q[2]); sc.qd = at(o_q[3]); sc.qe = at(o_q[4]);
+    bf16 *query = at(o_query), *qpos = at(o_qpos), *low_mem = at(o_lowmem), *high_mem = at(o_highmem);
+
+    // (1) VRT features -> decoder width; object queries                                          (:196-206)
+    RC(input_projection(h, (const bf16*)vrt_feats, n_vrt, at(o_ipn), at(o_iph), at(o_vp), st));
+    RC(launch_build_queries(h->dec_tokens3, at(o_vp), h->dec_vp_emb, I + i_qsrc, NQ, H, query, st));
+    PADT_CHECK_CUDA(cudaMemcpyAsync(qpos, query, (size_t)NQ * H * 2, cudaMemcpyDeviceToDevice, st));    // query_pos = initial queries (:216)
+    // (2) low-res memory: project once per image, replicate per object                          (:210, padt.py:370)
+    RC(input_projection(h, (const bf16*)low, M_all, at(o_ipn), at(o_iph), at(o_lowimg), st));
+    RC(launch_gather_rows(at(o_lowimg), H, I + i_lsrc, low_mem, H, NL, H, st));
+    // (3) low-res block                                                                          (:216)
+    Segs sl = {I + i_qoff, I + i_qlen, I + i_loff, I + i_llen, n_obj, max_q, max_l};
+    RC(dec_block(h, h->dec_blocks[0], query, NQ, low_mem, NL, qpos, sl, cos, sin, I + i_lpe, sc, st));
+    // (4) high-res memory = RMSNorm(repeat4(low) + high)                                         (:220)
+    RC(launch_add_rmsnorm_rep_map(low_mem, unit, (const bf16*)high, I + i_hsrc, h->dec_hr_norm, high_mem, NH, H, 1e-6f, st));
+    // (5) two high-res blocks                                                                    (:224-225)
+    Segs sh = {I + i_qoff, I + i_qlen, I + i_hoff, I + i_hlen, n_obj, max_q, max_h};
+    RC(dec_block(h, h->dec_blocks[1], query, NQ, high_mem, NH, qpos, sh, cos, sin, I + i_hsrc, sc, st));
+    RC(dec_block(h, h->dec_blocks[2], query, NQ, high_mem, NH, qpos, sh, cos, sin, I + i_hsrc, sc, st));
+    // (6) heads                                                                                  (:230-238)
+    bf16* tok = at(o_tok);
+    RC(launch_gather_rows(query, H, I + i_tok, tok, H, 3 * n_obj, H, st));
+    RC(mlp3(h, h->bbox_mlp, tok, n_obj, 4, at(o_t0), at(o_t1), (bf16*)boxes, st));
+    RC(launch_sigmoid((bf16*)boxes, (long long)n_obj * 4, st));
+    RC(gemm(EPI_NONE, tok + (size_t)n_obj * H, H, h->score_w, H, h->score_b, nullptr, 0, (bf16*)scores, 1, nullptr, n_obj, 1, H, st));
+    if (masks) {
+        RC(mlp3(h, h->mask_mlp, tok + (size_t)2 * n_obj * H, n_obj, H / 16, at(o_t0), at(o_t1), at(o_hyper), st));
+        // (7) mask embeddings                                                                    (:240-244)
+        RC(gemm(EPI_NONE, high_mem, H, h->up1_w, H, h->up1_b, nullptr, 0, sc.a, H, nullptr, NH, H, H, st));
+        RC(launch_rmsnorm(sc.a, H, h->up1_ln, sc.b, H, NH, H, 1e-6f, st));
+        RC(launch_gelu(sc.b, (long long)NH * H, st));
+        RC(gemm(EPI_GELU, sc.b, H / 4, h->up2_w, H / 4, h->up2_b, nullptr, 0, sc.c, H / 4, nullptr, NH * 4, H / 4, H / 4, st));
+        // (8) per-patch 4x4 logits + scatter                                                     (:246-274)
+        PADT_CHECK_CUDA(cudaMemsetAsync(masks, 0, (size_t)n_obj * 16 * hmax * wmax * 2, st));
+        RC(launch_mask_head(sc.c, at(o_hyper), I + i_cup, I + i_objw, n_obj, NH, H / 16, hmax, wmax, (bf16*)masks, st));
+    }
+    return 0;
+}

@@ -1,0 +1,184 @@
+// Dense projection  C[M,N] = A[M,K] * W[N,K]^T (+bias) with fused epilogues   (bf16 in, fp32 accumulate)
+//
+// Replaces every nn.Linear call of the reference's tensor-core-bound stages (cuBLAS via PyTorch in the
+// reference): ViT patch-embed / qkv / proj / MLP / merger (HF:91-146,207-322),
+// LLM prefill projections (HF:611-624,672-759), PaDT decoder projections (padt_decoder.py:11-60,82-86,142-184).
+// Rounding points are the HF ones: Linear output rounded to bf16 once (acc + bias in fp32), activation on the
+// rounded value, residual add rounded again.
+//
+// v1 kernel: mma.sync m16n8k16 tiles fed by a 4-stage cp.async pipeline, 128x128x32 CTA tile, XOR-swizzled smem.
+// (The tcgen05/TMA replacement for the large-M shapes is gemm_tc.cu.)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 4, THREADS = 256;
+constexpr int SMEM_BYTES = STAGES * (BM + BN) * BK * 2;
+
+__device__ __forceinline__ int swz(int row, int ch) { return ch ^ ((row >> 1) & 3); }
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(GemmParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    bf16* sA = reinterpret_cast<bf16*>(smem_raw);
+    bf16* sB = sA + STAGES * BM * BK;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nk = (p.K + BK - 1) / BK;
+
+    auto load_stage = [&](int s, int kt) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int id = tid + i * THREADS;
+            int row = id >> 2, ch = id & 3;
+            int gk = kt * BK + ch * 8;
+            int kb = (p.K - gk) * 2;
+            kb = kb < 0 ? 0 : (kb > 16 ? 16 : kb);
+            {
+                int gr = m0 + row;
+                int bytes = gr < p.M ? kb : 0;
+                const bf16* src = p.A + (size_t)(gr < p.M ? gr : 0) * p.lda + (bytes > 0 ? gk : 0);
+                cp_async16(sA + (s * BM + row) * BK + swz(row, ch) * 8, src, bytes);
+            }
+            {
+                int gr = n0 + row;
+                int bytes = gr < p.N ? kb : 0;
+                const bf16* src = p.W + (size_t)(gr < p.N ? gr : 0) * p.ldw + (bytes > 0 ? gk : 0);
+                cp_async16(sB + (s * BN + row) * BK + swz(row, ch) * 8, src, bytes);
+            }
+        }
+    };
+
+    float acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nx = kt + STAGES - 1;
+            if (nx < nk) load_stage(nx % STAGES, nx);
+            cp_async_commit();
+        }
+        const bf16* a_s = sA + (kt % STAGES) * BM * BK;
+        const bf16* b_s = sB + (kt % STAGES) * BN * BK;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+            uint32_t af[4][4], bfr[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                int row = wm * 64 + mi * 16 + (lane & 15);
+                int ch = kk * 2 + (lane >> 4);
+                ldmatrix_x4(af[mi][0], af[mi][1], af[mi][2], af[mi][3], a_s + row * BK + swz(row, ch) * 8);
+            }
+#pragma unroll
+            for (int nj = 0; nj < 2; ++nj) {
+                int row = wn * 32 + nj * 16 + (lane & 7) + ((lane >> 4) << 3);
+                int ch = kk * 2 + ((lane >> 3) & 1);
+                ldmatrix_x4(bfr[nj][0], bfr[nj][1], bfr[nj][2], bfr[nj][3], b_s + row * BK + swz(row, ch) * 8);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    mma_bf16_16816(acc[mi][ni], af[mi], bfr[ni >> 1][(ni & 1) * 2], bfr[ni >> 1][(ni & 1) * 2 + 1]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue
+    const int n_out = (EPI == EPI_SWIGLU) ? p.N / 2 : p.N;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            int row = m0 + wm * 64 + mi * 16 + (lane >> 2) + half * 8;
+            if (row >= p.M) continue;
+            int orow = p.out_row_map ? p.out_row_map[row] : row;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                int col = n0 + wn * 32 + ni * 8 + (lane & 3) * 2;
+                if (col >= p.N) continue;
+                float v0 = acc[mi][ni][half * 2 + 0], v1 = acc[mi][ni][half * 2 + 1];
+                bool has1 = (col + 1) < p.N;
+                if (p.bias) {
+                    v0 += bf2f(p.bias[col]);
+                    if (has1) v1 += bf2f(p.bias[col + 1]);
+                }
+                v0 = rbf(v0);
+                v1 = rbf(v1);
+                if (EPI == EPI_SWIGLU) {
+                    // interleaved rows: even = gate_j, odd = up_j  ->  bf16(bf16(silu(g)) * u)   (HF:88 / HF:623)
+                    float r = rbf(rbf(silu_f(v0)) * v1);
+                    p.C[(size_t)orow * p.ldc + (col >> 1)] = f2bf(r);
+                    continue;
+                }
+                if (EPI == EPI_GELU) {
+                    v0 = rbf(gelu_erf_f(v0));
+                    v1 = rbf(gelu_erf_f(v1));
+                }
+                if (EPI == EPI_RESID) {
+                    const bf16* r = p.resid + (size_t)orow * p.ldr + col;
+                    v0 = rbf(bf2f(r[0]) + v0);
+                    if (has1) v1 = rbf(bf2f(r[1]) + v1);
+                }
+                bf16* dst = p.C + (size_t)orow * p.ldc + col;
+                if (has1 && ((p.ldc & 1) == 0)) {
+                    *reinterpret_cast<uint32_t*>(dst) = f2_to_bf2x(v0, v1);
+                } else {
+                    dst[0] = f2bf(v0);
+                    if (has1) dst[1] = f2bf(v1);
+                }
+            }
+        }
+    }
+    (void)n_out;
+}
+
+template <int EPI>
+int launch_t(const GemmParams& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM));
+    gemm_bf16_kernel<EPI><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    PADT_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int launch_gemm(int epi, const GemmParams& p, cudaStream_t st) {
+    if (p.M == 0 || p.N == 0) return 0;
+    PADT_REQUIRE(p.K > 0, "K");
+    PADT_REQUIRE((p.lda % 8) == 0 && (p.ldw % 8) == 0, "lda/ldw must be multiples of 8 elements (16-byte rows)");
+    PADT_REQUIRE((((uintptr_t)p.A) & 15) == 0 && (((uintptr_t)p.W) & 15) == 0, "A/W must be 16-byte aligned");
+    PADT_REQUIRE(((uintptr_t)p.C & 3) == 0, "C must be 4-byte aligned");
+    switch (epi) {
+        case EPI_NONE: return launch_t<EPI_NONE>(p, st);
+        case EPI_GELU: return launch_t<EPI_GELU>(p, st);
+        case EPI_RESID:
+            PADT_REQUIRE(p.resid != nullptr, "resid");
+            return launch_t<EPI_RESID>(p, st);
+        case EPI_SWIGLU:
+            PADT_REQUIRE((p.N % 2) == 0, "interleaved gate/up needs even N");
+            return launch_t<EPI_SWIGLU>(p, st);
+    }
+    padt_set_error("launch_gemm: unknown epilogue");
+    return -1;
+}

@@ -1,0 +1,57 @@
+"""Shared helpers for the parity tests."""
+import math
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_golden(name):
+    return torch.load(os.path.join(ROOT, "tests", "golden", name + ".pt"), weights_only=False)
+
+
+def bf16_ulp(x: float) -> float:
+    """Spacing of bf16 numbers around |x| (8 significant bits)."""
+    ax = abs(float(x))
+    if ax == 0.0 or not math.isfinite(ax):
+        return 2.0 ** -133
+    return 2.0 ** (math.floor(math.log2(ax)) - 7)
+
+
+def close_report(a: torch.Tensor, b: torch.Tensor):
+    a32, b32 = a.detach().float().cpu().reshape(-1), b.detach().float().cpu().reshape(-1)
+    diff = (a32 - b32).abs()
+    scale = b32.abs().max().clamp_min(1e-12)
+    cos = torch.nn.functional.cosine_similarity(a32, b32, dim=0).item() if a32.numel() > 1 else 1.0
+    return dict(max_abs=float(diff.max()), rel_to_max=float(diff.max() / scale), mean_abs=float(diff.mean()), cos=cos,
+                frac_exact=float((a32 == b32).float().mean()))
+
+
+def assert_close_bf16(a, b, what, rel_to_max=0.03, cos=0.999):
+    """bf16 pipelines agree to accumulation-order noise: every intermediate is rounded to 8 bits, so after a stack of
+    layers elements differ by a few ulps of the *largest* magnitudes; we bound the worst element relative to max|ref|
+    and require near-perfect direction agreement."""
+    r = close_report(a, b)
+    assert r["rel_to_max"] <= rel_to_max and r["cos"] >= cos, f"{what}: {r}"
+    return r
+
+
+def check_tokens_margin(cand: torch.Tensor, ref: torch.Tensor, top2: torch.Tensor, what: str, ulps: float = 2.0):
+    """Greedy parity with a near-tie escape: a candidate arg-max may differ from the oracle's only where the oracle's own
+    top-1/top-2 logit gap is <= `ulps` bf16 ulps (an exact or 1-ulp tie that accumulation order can flip).
+    cand/ref [T,B] ints; top2 [T,B,2] oracle logits.  Returns (n_equal, n_tie_flips)."""
+    cand, ref = cand.cpu(), ref.cpu()
+    T, B = ref.shape
+    equal = flips = 0
+    for t in range(T):
+        for b in range(B):
+            if int(cand[t, b]) == int(ref[t, b]):
+                equal += 1
+                continue
+            v1, v2 = float(top2[t, b, 0]), float(top2[t, b, 1])
+            gap = v1 - v2
+            assert gap <= ulps * bf16_ulp(v1), (f"{what}: step {t} row {b}: candidate {int(cand[t, b])} != oracle {int(ref[t, b])} "
+                                                f"with oracle top-2 gap {gap} (> {ulps} bf16 ulps = {ulps * bf16_ulp(v1)})")
+            flips += 1
+    return equal, flips

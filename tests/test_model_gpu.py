@@ -1,0 +1,203 @@
+"""End-to-end parity (GPU): the CUDA path through the drop-in API against (a) the committed golden fixtures produced by the
+UNMODIFIED reference (oracle/make_golden.py) and (b) the oracle run on seeded inputs of a larger config.
+
+Token parity is greedy-exact with one documented escape: where the oracle's own top-1/top-2 logit gap is <= 2 bf16 ulps
+(random-init logits are almost flat, so exact/1-ulp ties are frequent) accumulation order may pick the other candidate.
+Floats: bf16 tensors are compared with a bound relative to max|ref| (see helpers.assert_close_bf16); boxes/scores/mask
+logits additionally report the 1e-3 criterion of the north star (bf16 resolution at 0.5 is 2e-3..4e-3, so it is applied as
+"<= 1e-3 or <= 2 bf16 ulps")."""
+import pytest
+import torch
+
+from helpers import assert_close_bf16, bf16_ulp, check_tokens_margin, close_report, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cfg, seed):
+    from padt_b200.modeling import PaDTForConditionalGeneration
+    from padt_b200.weights import random_weights
+    w_cpu = random_weights(cfg, seed=seed)
+    w = {k: v.cuda() for k, v in w_cpu.items()}
+    return PaDTForConditionalGeneration(cfg, w), w_cpu
+
+
+def _cfg_for(fx):
+    from padt_b200.config import padt_tiny
+    return padt_tiny(tie=fx["tie"], vocab=fx["vocab"])
+
+
+def _assert_box_like(a, b, what):
+    a32, b32 = a.float().cpu(), b.float().cpu()
+    d = (a32 - b32).abs()
+    tol = torch.tensor([max(1e-3, 2 * bf16_ulp(float(x))) for x in b32.reshape(-1)]).reshape(b32.shape)
+    assert bool((d <= tol).all()), f"{what}: max abs diff {float(d.max())}, worst tol {float(tol.max())}, n>1e-3: {int((d > 1e-3).sum())}/{d.numel()}"
+
+
+@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+def test_vit_against_reference_golden(name):
+    fx = load_golden(name)
+    model, _ = _model(_cfg_for(fx), fx["wseed"])
+    emb, high, (cos, sin) = model.engine.vit_forward(fx["pixel_values"].cuda(), fx["grid"])
+    torch.cuda.synchronize()
+    assert torch.equal(cos.cpu(), fx["cos"]) and torch.equal(sin.cpu(), fx["sin"]), "rotary tables must be bit-exact"
+    assert_close_bf16(high, fx["high_res"], "high_res (window order)")
+    assert_close_bf16(emb, fx["image_embeds"], "image_embeds (raster order)")
+    protos = model.engine.prototypes(emb)
+    torch.cuda.synchronize()
+    assert_close_bf16(protos, fx["prototypes"], "prototypes")
+
+
+@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+def test_generate_against_reference_golden(name):
+    fx = load_golden(name)
+    model, _ = _model(_cfg_for(fx), fx["wseed"])
+    steps = fx["steps"]
+    L = fx["input_ids"].shape[1]
+    out = model.generate(input_ids=fx["input_ids"].cuda(), attention_mask=fx["attention_mask"].cuda(), pixel_values=fx["pixel_values"].cuda(),
+                         image_grid_thw=fx["grid"].cuda(), max_new_tokens=steps, do_sample=False, output_hidden_states=True,
+                         return_dict_in_generate=True, eos_token_id=[])
+    seq = out.sequences.cpu()
+    assert seq.shape == fx["sequences"].shape
+    assert torch.equal(seq[:, :L], fx["input_ids"])
+    # free-running greedy: compare until the first divergence, which must be a near-tie of the reference's logits
+    cand, ref = seq[:, L:].t(), fx["sequences"][:, L:].t()
+    top2 = fx["top8_values"][:, :, :2]
+    for b in range(ref.shape[1]):
+        for t in range(steps):
+            if int(cand[t, b]) != int(ref[t, b]):
+                gap = float(top2[t, b, 0] - top2[t, b, 1])
+                assert gap <= 2 * bf16_ulp(float(top2[t, b, 0])), f"row {b} diverged at step {t} with reference gap {gap}"
+                break
+    # hidden state that predicted token 0 = last prompt position
+    assert_close_bf16(out.hidden_states[0][-1][:, -1, :], fx["last_hidden"][0], "prefill last hidden")
+    assert out.past_image_embeds.shape == fx["prototypes"].shape
+    assert out.past_logit_mask.shape == (fx["input_ids"].shape[0], fx["vocab"] + fx["prototypes"].shape[0])
+
+
+@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+def test_teacher_forced_against_reference_golden(name):
+    """Feeds the reference's forced token stream (half of it VRT ids of the row's own image) and compares, per step, the
+    arg-max and the final-norm hidden state with what the reference produced."""
+    fx = load_golden(name)
+    model, _ = _model(_cfg_for(fx), fx["wseed"])
+    steps = fx["steps"]
+    out = model.generate(input_ids=fx["input_ids"].cuda(), attention_mask=fx["attention_mask"].cuda(), pixel_values=fx["pixel_values"].cuda(),
+                         image_grid_thw=fx["grid"].cuda(), max_new_tokens=steps, do_sample=False, output_hidden_states=True,
+                         return_dict_in_generate=True, eos_token_id=[], forced_tokens=fx["forced"].cuda())
+    L = fx["input_ids"].shape[1]
+    assert torch.equal(out.sequences[:, L:].cpu(), fx["forced"]), "forced tokens are what gets appended"
+    eq, flips = check_tokens_margin(out.argmax_tokens.t(), fx["forced_argmax"], fx["forced_top2"], name)
+    assert eq >= 0.8 * (eq + flips), f"too many near-tie flips: {flips} of {eq + flips}"
+    for s in range(1, steps):
+        assert_close_bf16(out.hidden_states[s][-1][:, 0, :], fx["forced_last_hidden"][s], f"hidden step {s}")
+
+
+@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+def test_vl_decode_against_reference_golden(name):
+    fx = load_golden(name)
+    model, _ = _model(_cfg_for(fx), fx["wseed"])
+    steps = fx["steps"]
+    out = model.generate(input_ids=fx["input_ids"].cuda(), attention_mask=fx["attention_mask"].cuda(), pixel_values=fx["pixel_values"].cuda(),
+                         image_grid_thw=fx["grid"].cuda(), max_new_tokens=steps, do_sample=False, output_hidden_states=True,
+                         return_dict_in_generate=True, eos_token_id=[], forced_tokens=fx["forced"].cuda())
+    feats = []
+    for b, objs in enumerate(fx["objects"]):
+        feats.append([torch.cat([out.hidden_states[s][-1][b] for s in range(s0, s0 + n)], dim=0) for (s0, n) in objs])
+    dec = model.vl_decode(feats, out.past_image_embeds, out.past_high_res_image_embeds, fx["grid"].cuda(), out.past_visual_pe)
+    torch.cuda.synchronize()
+    assert dec["sample_idx"] == fx["sample_idx"]
+    assert torch.equal(dec["pred_mask_valid_hw"][0].cpu(), fx["Hs"]) and torch.equal(dec["pred_mask_valid_hw"][1].cpu(), fx["Ws"])
+    assert dec["pred_mask"].shape == fx["pred_mask"].shape
+    print(name, "boxes", close_report(dec["pred_boxes"], fx["pred_boxes"]), "mask", close_report(dec["pred_mask"], fx["pred_mask"]))
+    assert_close_bf16(dec["pred_boxes"], fx["pred_boxes"], "pred_boxes", rel_to_max=0.02)
+    assert_close_bf16(dec["pred_score"], fx["pred_score"], "pred_score", rel_to_max=0.05, cos=0.99)
+    assert_close_bf16(dec["pred_mask"], fx["pred_mask"], "pred_mask", rel_to_max=0.05, cos=0.995)
+    # zero padding outside each object's valid region is exact
+    for o in range(dec["pred_mask"].shape[0]):
+        h, w = int(fx["Hs"][o]) * 4, int(fx["Ws"][o]) * 4
+        assert float(dec["pred_mask"][o, h:, :].abs().max() if h < dec["pred_mask"].shape[1] else 0) == 0.0
+        assert float(dec["pred_mask"][o, :, w:].abs().max() if w < dec["pred_mask"].shape[2] else 0) == 0.0
+
+
+def test_vl_decode_empty():
+    fx = load_golden("tiny_b1")
+    model, _ = _model(_cfg_for(fx), fx["wseed"])
+    dec = model.vl_decode([[]], torch.zeros((24, 256), device="cuda", dtype=torch.bfloat16), torch.zeros((96, 160), device="cuda", dtype=torch.bfloat16),
+                          fx["grid"].cuda(), (torch.zeros((96, 80), device="cuda"), torch.zeros((96, 80), device="cuda")))
+    assert dec["pred_boxes"].shape == (0, 4) and dec["pred_mask"].shape == (0, 8, 8) and dec["sample_idx"] == [] and dec["pred_mask_valid_hw"] == ()
+
+
+def test_eos_stops_and_pads():
+    """Finished rows emit pad tokens until every row is finished (padt.py:748-757)."""
+    fx = load_golden("tiny_b2")
+    cfg = _cfg_for(fx)
+    model, _ = _model(cfg, fx["wseed"])
+    L = fx["input_ids"].shape[1]
+    ref = fx["sequences"][:, L:]
+    eos0 = int(ref[0, 2])                       # make row 0 stop at its 3rd token
+    out = model.generate(input_ids=fx["input_ids"].cuda(), attention_mask=fx["attention_mask"].cuda(), pixel_values=fx["pixel_values"].cuda(),
+                         image_grid_thw=fx["grid"].cuda(), max_new_tokens=fx["steps"], do_sample=False, return_dict_in_generate=True,
+                         eos_token_id=[eos0], pad_token_id=cfg.pad_token_id)
+    gen = out.sequences[:, L:].cpu()
+    row0 = gen[0].tolist()
+    first = row0.index(eos0)
+    assert all(t == cfg.pad_token_id for t in row0[first + 1:]), row0
+
+
+def test_small_config_against_oracle():
+    """GQA group 4, untied head, 4 layers, two images with different grids: CUDA path vs the CPU oracle on seeded inputs."""
+    import padt_oracle as O
+    from padt_b200.config import padt_small
+    cfg = padt_small()
+    model, w_cpu = _model(cfg, 3)
+    g = torch.Generator().manual_seed(5)
+    grids = [(1, 12, 20), (1, 8, 8)]
+    V = cfg.text.vocab_size
+    rows = []
+    for (t, h, w), pl in zip(grids, [7, 12]):
+        M = t * h * w // 4
+        rows.append(torch.randint(0, V - 16, (3,), generator=g).tolist() + [cfg.vision_start_token_id] + [cfg.image_token_id] * M +
+                    [cfg.vision_end_token_id] + torch.randint(0, V - 16, (pl,), generator=g).tolist())
+    L = max(len(r) for r in rows)
+    ids = torch.full((2, L), cfg.pad_token_id, dtype=torch.long)
+    mask = torch.zeros((2, L), dtype=torch.long)
+    for i, r in enumerate(rows):
+        ids[i, L - len(r):] = torch.tensor(r); mask[i, L - len(r):] = 1
+    pv = torch.randn((sum(t * h * w for t, h, w in grids), cfg.vision.patch_dim), generator=g).to(torch.bfloat16)
+    grid = torch.tensor(grids)
+    steps = 8
+    off = O.patch_offsets(cfg, grid)
+    forced = torch.randint(0, V - 16, (2, steps), generator=g)
+    for b in range(2):
+        forced[b, ::2] = V + off[b] + torch.randint(0, off[b + 1] - off[b], (steps // 2,), generator=g)
+    ref = O.greedy_generate(w_cpu, cfg, ids, mask, pv, grid, steps, eos_token_ids=[], forced_tokens=forced)
+    out = model.generate(input_ids=ids.cuda(), attention_mask=mask.cuda(), pixel_values=pv.cuda(), image_grid_thw=grid.cuda(),
+                         max_new_tokens=steps, output_hidden_states=True, return_dict_in_generate=True, eos_token_id=[], forced_tokens=forced.cuda())
+    assert_close_bf16(out.past_high_res_image_embeds, ref["past_high_res_image_embeds"], "high_res")
+    assert_close_bf16(out.past_image_embeds, ref["past_image_embeds"], "prototypes")
+    top2 = torch.stack([torch.topk(l, 2, dim=-1).values for l in ref["logits_steps"]])
+    eq, flips = check_tokens_margin(out.argmax_tokens.t(), torch.stack(ref["argmax_steps"]), top2, "small")
+    assert eq >= 0.8 * (eq + flips)
+    for s in range(1, steps):
+        assert_close_bf16(out.hidden_states[s][-1][:, 0, :], ref["hidden_steps"][s][:, -1, :], f"hidden step {s}")
+    feats_ref = [[torch.cat([ref["hidden_steps"][s][b] for s in (1, 2)], 0)] for b in range(2)]
+    feats = [[torch.cat([out.hidden_states[s][-1][b] for s in (1, 2)], 0)] for b in range(2)]
+    d_ref = O.vl_decode(w_cpu, cfg, feats_ref, ref["past_image_embeds"], ref["past_high_res_image_embeds"], grid, ref["past_visual_pe"])
+    d = model.vl_decode(feats, out.past_image_embeds, out.past_high_res_image_embeds, grid.cuda(), out.past_visual_pe)
+    print("small boxes", close_report(d["pred_boxes"], d_ref["pred_boxes"]), "mask", close_report(d["pred_mask"], d_ref["pred_mask"]))
+    assert_close_bf16(d["pred_boxes"], d_ref["pred_boxes"], "boxes", rel_to_max=0.02)
+    assert_close_bf16(d["pred_mask"], d_ref["pred_mask"], "mask", rel_to_max=0.06, cos=0.995)
+
+
+def test_graph_and_eager_decode_agree():
+    fx = load_golden("tiny_b1")
+    model, _ = _model(_cfg_for(fx), fx["wseed"])
+    kw = dict(input_ids=fx["input_ids"].cuda(), attention_mask=fx["attention_mask"].cuda(), pixel_values=fx["pixel_values"].cuda(),
+              image_grid_thw=fx["grid"].cuda(), max_new_tokens=fx["steps"], return_dict_in_generate=True, eos_token_id=[],
+              forced_tokens=fx["forced"].cuda(), output_hidden_states=True)
+    a = model.generate(**kw)
+    model.engine.set_option("use_graph", 0)
+    b = model.generate(**kw)
+    assert torch.equal(a.argmax_tokens, b.argmax_tokens)
+    assert torch.equal(a.hidden_states[-1][-1], b.hidden_states[-1][-1])
