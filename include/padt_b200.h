@@ -60,6 +60,12 @@ int padt_vit_forward(PadtHandle* h, const void* pixel_values, const int64_t* gri
                      const float* pos_sin, int tab_rows, void* image_embeds, void* high_res, float* cos, float* sin,
                      padt_stream_t stream);
 
+/* V3/V4 host integer tables only (no GPU needed): rot_pos_emb / get_window_index (HF:382-453) as the engine builds them.
+ * embed_row_map[P]: window-order row of each input patch; hpos/wpos[P]: rotary ids in window order; merge_row_map[M] ==
+ * window_index; win_len[n_win] patches per (non-empty) window.  Any output pointer may be NULL. */
+int padt_vit_plan_host(const PadtDims* dims, const int64_t* grid_thw_host, int n_img, int32_t* embed_row_map, int32_t* hpos,
+                       int32_t* wpos, int32_t* merge_row_map, int32_t* win_len, int32_t* n_win, int32_t* n_patches);
+
 /* E1: prototype projection (padt.py:187-191). */
 int padt_prototypes(PadtHandle* h, const void* image_embeds, int n_rows, void* prototypes, padt_stream_t stream);
 

@@ -73,6 +73,8 @@ struct PadtHandle {
     int use_graph = 1;
     cudaGraphExec_t step_graph = nullptr;
     int graph_kernels = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     const void* graph_key_protos = nullptr;
     int graph_key_B = 0;
     DevBuf eos_dev;

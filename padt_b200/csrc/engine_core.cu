@@ -214,6 +214,7 @@ extern "C" int padt_destroy(PadtHandle* h) {
     if (!h) return 0;
     cudaDeviceSynchronize();
     if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+    if (h->own_stream) { cudaStreamDestroy(h->own_stream); cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_out); }
     for (auto& kv : h->vit_plans) { kv.second->ints.release(); delete kv.second; }
     for (DevBuf* b : {&h->arena, &h->vit_ws, &h->proto_ws, &h->llm_ws, &h->kv, &h->dec_ws, &h->state, &h->seg_ints, &h->eos_dev, &h->dec_dws,
                       &h->dec_ints})

@@ -152,7 +152,17 @@ extern "C" int padt_prefill(PadtHandle* h, const int64_t* input_ids, const int32
 
 extern "C" int padt_decode(PadtHandle* h, int n_steps, int finish, padt_stream_t stream) {
     PADT_REQUIRE(h && h->gen_ready, "padt_prefill must run first");
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t caller = (cudaStream_t)stream;
+    // Stream capture is illegal on the legacy default stream (which is what torch hands out by default), so the decode loop
+    // runs on an engine-owned non-blocking stream, ordered after / before the caller's stream with events.
+    if (!h->own_stream) {
+        PADT_CHECK_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        PADT_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        PADT_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    }
+    cudaStream_t st = h->own_stream;
+    PADT_CHECK_CUDA(cudaEventRecord(h->ev_in, caller));
+    PADT_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_in, 0));
     int s = 0;
     if (n_steps > 0 && h->use_graph && !h->step_graph) {
         // first step runs eagerly (also performs the one-time cudaFuncSetAttribute calls), later steps replay a graph of it;
@@ -178,6 +188,8 @@ extern "C" int padt_decode(PadtHandle* h, int n_steps, int finish, padt_stream_t
         else RC(run_step(h, st));
     }
     if (finish) RC(launch_sample_embed(h->dp, st));
+    PADT_CHECK_CUDA(cudaEventRecord(h->ev_out, st));
+    PADT_CHECK_CUDA(cudaStreamWaitEvent(caller, h->ev_out, 0));
     return 0;
 }
 

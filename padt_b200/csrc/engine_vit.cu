@@ -1,6 +1,7 @@
 // ViT patch encoder + VRT prototype projection (host orchestration).
 // Reference: custom_visual_forward padt.py:48-106 (HF:91-146,207-322,382-453) and padt.py:187-191.
 #include "engine.h"
+#include <algorithm>
 
 namespace {
 
@@ -86,6 +87,24 @@ int get_plan(PadtHandle* h, const int64_t* grid, int n_img, VitPlan** out, cudaS
 }
 
 }  // namespace
+
+// Host-only: the integer tables of V3/V4 (window permutation, rotary position ids, segment lengths) for one grid list.
+// Sizes: embed_row_map/hpos/wpos [P], merge_row_map [M], win_len [<= M]; returns the number of windows via *n_win.
+extern "C" int padt_vit_plan_host(const PadtDims* dims, const int64_t* grid_thw_host, int n_img, int32_t* embed_row_map, int32_t* hpos,
+                                  int32_t* wpos, int32_t* merge_row_map, int32_t* win_len, int32_t* n_win, int32_t* n_patches) {
+    PADT_REQUIRE(dims && grid_thw_host && n_win && n_patches, "null argument");
+    HostPlan hp;
+    int P, M;
+    build_host_plan(*dims, grid_thw_host, n_img, hp, P, M);
+    *n_patches = P;
+    *n_win = (int)hp.win_len.size();
+    if (embed_row_map) std::copy(hp.embed_row_map.begin(), hp.embed_row_map.end(), embed_row_map);
+    if (hpos) std::copy(hp.hpos.begin(), hp.hpos.end(), hpos);
+    if (wpos) std::copy(hp.wpos.begin(), hp.wpos.end(), wpos);
+    if (merge_row_map) std::copy(hp.merge_row_map.begin(), hp.merge_row_map.end(), merge_row_map);
+    if (win_len) std::copy(hp.win_len.begin(), hp.win_len.end(), win_len);
+    return 0;
+}
 
 extern "C" int padt_vit_forward(PadtHandle* h, const void* pixel_values, const int64_t* grid_thw_host, int n_img, const float* pos_cos,
                                 const float* pos_sin, int tab_rows, void* image_embeds, void* high_res, float* cos, float* sin,

@@ -1,0 +1,68 @@
+"""CPU: the oracle restatement reproduces, bit for bit, what the UNMODIFIED reference produced (tests/golden/*.pt written by
+oracle/make_golden.py in the build container).  This is what pins the oracle (the reference ships no numeric
+golden vectors of its own)."""
+import pytest
+import torch
+
+import padt_oracle as O
+from helpers import load_golden
+from padt_b200.config import padt_tiny
+from padt_b200.weights import random_weights
+
+
+def _eq(a, b):
+    return bool(((a == b) | (torch.isinf(a.float()) & torch.isinf(b.float()))).all()) and a.shape == b.shape
+
+
+@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+def test_oracle_reproduces_reference(name):
+    fx = load_golden(name)
+    cfg = padt_tiny(tie=fx["tie"], vocab=fx["vocab"])
+    w = random_weights(cfg, seed=fx["wseed"])
+    with torch.no_grad():
+        emb, high, (cos, sin) = O.vit_forward(w, cfg, fx["pixel_values"], fx["grid"])
+        assert _eq(emb, fx["image_embeds"]) and _eq(high, fx["high_res"]) and _eq(cos, fx["cos"]) and _eq(sin, fx["sin"])
+        g = O.greedy_generate(w, cfg, fx["input_ids"], fx["attention_mask"], fx["pixel_values"], fx["grid"], fx["steps"], eos_token_ids=[])
+        assert torch.equal(g["sequences"], fx["sequences"])
+        assert _eq(g["past_image_embeds"], fx["prototypes"])
+        last = torch.stack([h[:, -1, :] for h in g["hidden_steps"]])
+        assert _eq(last, fx["last_hidden"])
+        top = [torch.topk(l, 8, dim=-1) for l in g["logits_steps"]]
+        assert _eq(torch.stack([t.values for t in top]), fx["top8_values"])
+        f = O.greedy_generate(w, cfg, fx["input_ids"], fx["attention_mask"], fx["pixel_values"], fx["grid"], fx["steps"], eos_token_ids=[],
+                              forced_tokens=fx["forced"])
+        assert torch.equal(torch.stack(f["argmax_steps"]), fx["forced_argmax"])
+        assert _eq(torch.stack([h[:, -1, :] for h in f["hidden_steps"]]), fx["forced_last_hidden"])
+        feats = [[torch.cat([f["hidden_steps"][s][b] for s in range(s0, s0 + n)], dim=0) for (s0, n) in objs] for b, objs in enumerate(fx["objects"])]
+        d = O.vl_decode(w, cfg, feats, f["past_image_embeds"], f["past_high_res_image_embeds"], fx["grid"], f["past_visual_pe"])
+        assert _eq(d["pred_boxes"], fx["pred_boxes"]) and _eq(d["pred_score"], fx["pred_score"]) and _eq(d["pred_mask"], fx["pred_mask"])
+        assert torch.equal(d["pred_mask_valid_hw"][0], fx["Hs"]) and torch.equal(d["pred_mask_valid_hw"][1], fx["Ws"])
+        assert d["sample_idx"] == fx["sample_idx"]
+
+
+def test_extended_vocabulary_kat():
+    """V=512, two images M=(24, 8): logits width 544; finite columns row 0 -> 512+24, row 1 -> 512+8 at [536, 543]."""
+    fx = load_golden("tiny_b2")
+    cfg = padt_tiny(tie=fx["tie"], vocab=fx["vocab"])
+    mask = O.build_logit_mask(cfg, fx["grid"], 512 + 32)
+    assert mask.shape == (2, 544)
+    assert int(mask[0].sum()) == 512 + 24 and int(mask[1].sum()) == 512 + 8
+    assert mask[1, 536:544].all() and not mask[1, 512:536].any() and not mask[0, 536:].any()
+
+
+def test_vl_decode_empty_and_toy_shapes():
+    cfg = padt_tiny()
+    w = random_weights(cfg, seed=0)
+    d = O.vl_decode(w, cfg, [[]], torch.zeros((24, 256), dtype=torch.bfloat16), torch.zeros((96, 160), dtype=torch.bfloat16),
+                    torch.tensor([[1, 8, 12]]), (torch.zeros((96, 80)), torch.zeros((96, 80))))
+    assert d["pred_boxes"].shape == (0, 4) and d["pred_mask"].shape == (0, 8, 8) and d["sample_idx"] == []
+    g = torch.Generator().manual_seed(0)
+    feats = [[torch.randn((2, 256), generator=g).to(torch.bfloat16)]]
+    low = torch.randn((24, 256), generator=g).to(torch.bfloat16)
+    high = torch.randn((96, 160), generator=g).to(torch.bfloat16)
+    pe = (torch.rand((96, 80), generator=g), torch.rand((96, 80), generator=g))
+    d = O.vl_decode(w, cfg, feats, low, high, torch.tensor([[1, 8, 12]]), pe)
+    # Appendix A toy case: 1 image 8x12 patches, 1 object
+    assert d["pred_boxes"].shape == (1, 4) and d["pred_score"].shape == (1, 1) and d["pred_mask"].shape == (1, 32, 48)
+    assert d["pred_mask_valid_hw"][0].tolist() == [8] and d["pred_mask_valid_hw"][1].tolist() == [12] and d["sample_idx"] == [0]
+    assert float(d["pred_boxes"].min()) > 0 and float(d["pred_boxes"].max()) < 1
