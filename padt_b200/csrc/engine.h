@@ -71,6 +71,9 @@ struct PadtHandle {
     int gen_B = 0, gen_L = 0, s_max = 0;
     bool gen_ready = false;
     int use_graph = 1;
+    int decode_impl = 1;             // 1 = persistent kernel (decode_mega.cu) when it fits, 0 = per-layer kernels (decode.cu)
+    int n_sms = 0;
+    DevBuf llm_dev, gbar;
     cudaGraphExec_t step_graph = nullptr;
     int graph_kernels = 0;
     cudaStream_t own_stream = nullptr;

@@ -206,6 +206,14 @@ extern "C" int padt_create(const PadtDims* dims, const void* const* weights, int
     h->max_pos = max_pos;
     int rc = engine_build_weights(h);
     if (rc) { delete h; return rc; }
+    {   // device copy of the per-layer pointer table + grid-barrier word for the persistent decode kernel
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (h->llm_dev.ensure(h->llm.size() * sizeof(DecodeLayerW)) || h->gbar.ensure(256)) { delete h; return -2; }
+        cudaMemcpy(h->llm_dev.p, h->llm.data(), h->llm.size() * sizeof(DecodeLayerW), cudaMemcpyHostToDevice);
+        cudaMemset(h->gbar.p, 0, 256);
+    }
     *out = h;
     return 0;
 }
@@ -217,7 +225,7 @@ extern "C" int padt_destroy(PadtHandle* h) {
     if (h->own_stream) { cudaStreamDestroy(h->own_stream); cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_out); }
     for (auto& kv : h->vit_plans) { kv.second->ints.release(); delete kv.second; }
     for (DevBuf* b : {&h->arena, &h->vit_ws, &h->proto_ws, &h->llm_ws, &h->kv, &h->dec_ws, &h->state, &h->seg_ints, &h->eos_dev, &h->dec_dws,
-                      &h->dec_ints})
+                      &h->dec_ints, &h->llm_dev, &h->gbar})
         b->release();
     delete h;
     return 0;
@@ -227,6 +235,11 @@ extern "C" int padt_set_option(PadtHandle* h, const char* name, int value) {
     PADT_REQUIRE(h && name, "null");
     std::string n(name);
     if (n == "use_graph") { h->use_graph = value; return 0; }
+    if (n == "decode_impl") {
+        h->decode_impl = value;
+        if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
+        return 0;
+    }
     padt_set_error("unknown option " + n);
     return -1;
 }

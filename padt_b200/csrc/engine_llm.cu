@@ -13,8 +13,12 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     p.layers = h->llm.data();
     p.final_norm = h->final_norm; p.head = h->head; p.embed = h->embed; p.protos = (const bf16*)prototypes;
     p.cos_tab = h->cos_tab; p.sin_tab = h->sin_tab; p.max_pos = h->max_pos;
-    p.n_split = 16;
+    {   // split-KV factor: enough (row, kv head, split) items to cover the SMs, capped at 64 partials per head
+        int ns = h->n_sms / (B * d.n_kv_heads);
+        p.n_split = ns < 1 ? 1 : (ns > 64 ? 64 : ns);
+    }
     p.n_amax_blocks = decode_logits_blocks(d.vocab + n_protos);
+    if (p.n_amax_blocks < h->n_sms) p.n_amax_blocks = h->n_sms;
     // decode workspace: h [B,D] | qkv | act | part_o | part_ml | amax_val | amax_idx | counters | cur_token
     const int qkv_n = (d.n_heads + 2 * d.n_kv_heads) * h->hd;
     const int act_n = d.I > d.n_heads * h->hd ? d.I : d.n_heads * h->hd;
@@ -45,6 +49,12 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
 }
 
 int run_step(PadtHandle* h, cudaStream_t st) {
+    if (h->decode_impl == 1) {
+        int sb, ns, xb;
+        size_t smem;
+        if (decode_mega_plan(h->dp, &sb, &ns, &xb, &smem) == 0)
+            return launch_decode_mega(h->dp, h->llm_dev.as<DecodeLayerW>(), h->gbar.as<unsigned int>(), h->n_sms, st);
+    }
     RC(launch_sample_embed(h->dp, st));
     RC(launch_decode_layers(h->dp, st));
     RC(launch_final_logits(h->dp, st));

@@ -85,3 +85,6 @@ int decode_logits_blocks(int n_rows);
 int launch_sample_embed(const DecodeParams& p, cudaStream_t st);
 int launch_final_logits(const DecodeParams& p, cudaStream_t st);
 int launch_decode_layers(const DecodeParams& p, cudaStream_t st);
+// persistent one-launch-per-token kernel (decode_mega.cu)
+int decode_mega_plan(const DecodeParams& p, int* slot_bytes, int* n_slots, int* x_bytes, size_t* smem_bytes);
+int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, unsigned int* gbar, int n_sms, cudaStream_t st);

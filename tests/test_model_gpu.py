@@ -201,3 +201,28 @@ def test_graph_and_eager_decode_agree():
     b = model.generate(**kw)
     assert torch.equal(a.argmax_tokens, b.argmax_tokens)
     assert torch.equal(a.hidden_states[-1][-1], b.hidden_states[-1][-1])
+
+
+@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+def test_persistent_decode_kernel_bit_matches_per_layer_kernels(name):
+    """decode_mega.cu (one persistent launch per token, TMA-streamed weights) and decode.cu (5 kernels per layer) share
+    their device arithmetic, so tokens AND hidden states must be bit-identical."""
+    fx = load_golden(name)
+    model, _ = _model(_cfg_for(fx), fx["wseed"])
+    kw = dict(input_ids=fx["input_ids"].cuda(), attention_mask=fx["attention_mask"].cuda(), pixel_values=fx["pixel_values"].cuda(),
+              image_grid_thw=fx["grid"].cuda(), max_new_tokens=fx["steps"], return_dict_in_generate=True, eos_token_id=[],
+              forced_tokens=fx["forced"].cuda(), output_hidden_states=True)
+    model.engine.set_option("decode_impl", 1)
+    a = model.generate(**kw)
+    model.engine.set_option("decode_impl", 0)
+    b = model.generate(**kw)
+    assert torch.equal(a.argmax_tokens, b.argmax_tokens)
+    for s in range(1, fx["steps"]):
+        assert torch.equal(a.hidden_states[s][-1], b.hidden_states[s][-1]), f"hidden step {s}"
+    # and free-running
+    kw.pop("forced_tokens")
+    model.engine.set_option("decode_impl", 1)
+    a = model.generate(**kw)
+    model.engine.set_option("decode_impl", 0)
+    b = model.generate(**kw)
+    assert torch.equal(a.sequences, b.sequences)
