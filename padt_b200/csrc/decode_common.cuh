@@ -14,28 +14,31 @@ __device__ __host__ inline int st_vlo(int b) { return ST_HDR + 2 * ST_BMAX + b; 
 __device__ __host__ inline int st_vhi(int b) { return ST_HDR + 3 * ST_BMAX + b; }
 __device__ __host__ inline int st_unfin(int b) { return ST_HDR + 4 * ST_BMAX + b; }
 
+// 8 weights x NB activation rows.  Two independent accumulators per output (even / odd elements) halve the dependent FMA
+// chain; every decode path goes through this function, so they all share one summation order.
 template <int NB>
-__device__ __forceinline__ void dot8(const uint4& w, const bf16* xs, int K, int c, float* acc) {
+__device__ __forceinline__ void dot8(const uint4& w, const bf16* xs, int K, int c, float2* acc) {
     float2 w0 = bf2x_to_f2(w.x), w1 = bf2x_to_f2(w.y), w2 = bf2x_to_f2(w.z), w3 = bf2x_to_f2(w.w);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)b * K + c * 8);
         float2 x0 = bf2x_to_f2(xv.x), x1 = bf2x_to_f2(xv.y), x2 = bf2x_to_f2(xv.z), x3 = bf2x_to_f2(xv.w);
-        float a = acc[b];
-        a = fmaf(w0.x, x0.x, a); a = fmaf(w0.y, x0.y, a);
-        a = fmaf(w1.x, x1.x, a); a = fmaf(w1.y, x1.y, a);
-        a = fmaf(w2.x, x2.x, a); a = fmaf(w2.y, x2.y, a);
-        a = fmaf(w3.x, x3.x, a); a = fmaf(w3.y, x3.y, a);
+        float2 a = acc[b];
+        a.x = fmaf(w0.x, x0.x, a.x); a.y = fmaf(w0.y, x0.y, a.y);
+        a.x = fmaf(w1.x, x1.x, a.x); a.y = fmaf(w1.y, x1.y, a.y);
+        a.x = fmaf(w2.x, x2.x, a.x); a.y = fmaf(w2.y, x2.y, a.y);
+        a.x = fmaf(w3.x, x3.x, a.x); a.y = fmaf(w3.y, x3.y, a.y);
         acc[b] = a;
     }
 }
 
-// One warp computes two weight rows against NB activation rows held in shared memory.
+// One warp computes two weight rows (global memory) against NB activation rows held in shared memory.
 template <int NB>
 __device__ __forceinline__ void warp_rows2(const bf16* __restrict__ r0, const bf16* __restrict__ r1, int K, const bf16* xs, int lane,
-                                           float* acc0, float* acc1) {
+                                           float* out0, float* out1) {
+    float2 acc0[NB], acc1[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+    for (int b = 0; b < NB; ++b) { acc0[b] = make_float2(0.f, 0.f); acc1[b] = make_float2(0.f, 0.f); }
     const int nch = K >> 3;
     int c = lane;
     for (; c + 96 < nch; c += 128) {
@@ -55,9 +58,8 @@ __device__ __forceinline__ void warp_rows2(const bf16* __restrict__ r0, const bf
         dot8<NB>(b0, xs, K, c, acc1);
     }
 #pragma unroll
-    for (int b = 0; b < NB; ++b) { acc0[b] = warp_sum(acc0[b]); acc1[b] = warp_sum(acc1[b]); }
+    for (int b = 0; b < NB; ++b) { out0[b] = warp_sum(acc0[b].x + acc0[b].y); out1[b] = warp_sum(acc1[b].x + acc1[b].y); }
 }
-
 
 struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 // named barrier over the first `N` threads of the block (the persistent kernel keeps its producer warp out of it)
@@ -144,7 +146,8 @@ struct DecAttnArgs {
 };
 
 template <class Sync>
-__device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split, int kvh, int b, uint8_t* smem_raw, int tid, Sync sync) {
+__device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split, int kvh, int b, uint8_t* smem_raw, int tid, int nthreads,
+                                                 Sync sync) {
     bf16* sK = reinterpret_cast<bf16*>(smem_raw);           // [64][136]
     bf16* sV = sK + DA_TILE * DA_LD;                        // [64][136]
     float* sQ = reinterpret_cast<float*>(sV + DA_TILE * DA_LD);  // [group][128]
@@ -170,7 +173,7 @@ __device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split
     bf16* vc = a.vcache + ((size_t)b * a.nkv + kvh) * a.s_max * DA_HD;
 
     // ---- roped queries of this kv group -> sQ (fp32 values of the bf16-rounded result)
-    for (int i = tid; i < group * 64; i += DA_THREADS) {
+    for (int i = tid; i < group * 64; i += nthreads) {
         int g = i >> 6, j = i & 63;
         const bf16* q = row + (size_t)(kvh * group + g) * DA_HD;
         float c = bf2f(a.cos_tab[(size_t)pos * 64 + j]), sn = bf2f(a.sin_tab[(size_t)pos * 64 + j]);
@@ -184,7 +187,7 @@ __device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t0 = k_begin; t0 < k_end; t0 += DA_TILE) {
         sync();   // previous tile fully consumed (also orders the sQ writes on the first pass)
-        for (int id = tid; id < DA_TILE * 16; id += DA_THREADS) {
+        for (int id = tid; id < DA_TILE * 16; id += nthreads) {
             int r = id >> 4, c = id & 15;
             int key = t0 + r;
             bool ok = key < k_end && key != cur;
@@ -270,26 +273,61 @@ __device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split
         if (s_last) a.counters[b * a.nkv + kvh] = 0;   // re-arm for the next launch
     }
     sync();
-    if (s_last) __threadfence();
-    if (s_last && warp < group) {
-        int head = kvh * group + warp;
-        size_t base = ((size_t)b * a.nh + head) * a.n_split;
-        float M = -INFINITY;
-        for (int c = 0; c < a.n_split; ++c) M = fmaxf(M, __ldcg(a.part_ml + (base + c) * 2));
-        float Ls = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < a.n_split; ++c) {
-            float m = __ldcg(a.part_ml + (base + c) * 2), l = __ldcg(a.part_ml + (base + c) * 2 + 1);
-            if (m == -INFINITY) continue;
-            float w = exp2f(m - M);
-            Ls += l * w;
-            float4 po = __ldcg(reinterpret_cast<const float4*>(a.part_o + (base + c) * DA_HD + lane * 4));
-            o[0] += po.x * w; o[1] += po.y * w; o[2] += po.z * w; o[3] += po.w * w;
+    if (s_last) {
+        // ---- combine the split partials of this (row, kv head); with >= 2*group warps each head is shared by two warps
+        __threadfence();
+        float (*s_comb)[32][6] = reinterpret_cast<float (*)[32][6]>(smem_raw);   // K/V tiles are dead by now: reuse them
+        const int nw = nthreads >> 5;
+        const int halves = nw >= 2 * group ? 2 : 1;
+        const int hl = warp % group, half = warp / group;
+        const bool active = warp < group * halves;
+        const int per = (a.n_split + halves - 1) / halves;
+        const int c_lo = half * per, c_hi = (c_lo + per) < a.n_split ? (c_lo + per) : a.n_split;
+        const int head = kvh * group + hl;
+        const size_t base = ((size_t)b * a.nh + head) * a.n_split;
+        float M = -INFINITY, Ls = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (active) {
+            const float* ml = a.part_ml + base * 2;
+            int c0 = c_lo + lane, c1 = c_lo + lane + 32;
+            float m0 = c0 < c_hi ? __ldcg(ml + c0 * 2) : -INFINITY, l0 = c0 < c_hi ? __ldcg(ml + c0 * 2 + 1) : 0.f;
+            float m1 = c1 < c_hi ? __ldcg(ml + c1 * 2) : -INFINITY, l1 = c1 < c_hi ? __ldcg(ml + c1 * 2 + 1) : 0.f;
+            M = warp_max(fmaxf(m0, m1));
+            float w0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - M), w1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - M);
+            Ls = warp_sum(l0 * w0 + l1 * w1);
+            const float4* po = reinterpret_cast<const float4*>(a.part_o + base * DA_HD) + lane;
+            for (int cb = c_lo; cb < c_hi; cb += 16) {
+                float4 v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = (cb + k < c_hi) ? __ldcg(po + (size_t)(cb + k) * (DA_HD / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    int c = cb + k - c_lo;
+                    float w = __shfl_sync(0xffffffffu, c < 32 ? w0 : w1, c & 31);
+                    o[0] += v[k].x * w; o[1] += v[k].y * w; o[2] += v[k].z * w; o[3] += v[k].w * w;
+                }
+            }
+            if (half == 1) {
+                float* d = s_comb[hl][lane];
+                d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; d[3] = o[3]; d[4] = M; d[5] = Ls;
+            }
         }
-        float inv = Ls > 0.f ? 1.0f / Ls : 0.f;
-        uint2 pk;
-        pk.x = f2_to_bf2x(o[0] * inv, o[1] * inv);
-        pk.y = f2_to_bf2x(o[2] * inv, o[3] * inv);
-        *reinterpret_cast<uint2*>(a.out + (size_t)b * a.nh * DA_HD + (size_t)head * DA_HD + lane * 4) = pk;
+        if (halves == 2) sync();
+        if (active && half == 0) {
+            if (halves == 2) {
+                const float* d = s_comb[hl][lane];
+                float M1 = d[4], L1 = d[5];
+                float Mn = fmaxf(M, M1);
+                float f0 = (M == -INFINITY) ? 0.f : exp2f(M - Mn), f1 = (M1 == -INFINITY) ? 0.f : exp2f(M1 - Mn);
+                Ls = Ls * f0 + L1 * f1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = o[k] * f0 + d[k] * f1;
+            }
+            float inv = Ls > 0.f ? 1.0f / Ls : 0.f;
+            uint2 pk;
+            pk.x = f2_to_bf2x(o[0] * inv, o[1] * inv);
+            pk.y = f2_to_bf2x(o[2] * inv, o[3] * inv);
+            *reinterpret_cast<uint2*>(a.out + (size_t)b * a.nh * DA_HD + (size_t)head * DA_HD + lane * 4) = pk;
+        }
     }
 }
 

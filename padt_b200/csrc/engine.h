@@ -61,7 +61,7 @@ struct PadtHandle {
     DevBuf proto_ws;
     // LLM
     std::vector<DecodeLayerW> llm;
-    const bf16 *final_norm, *head, *embed;
+    const bf16 *final_norm, *head, *embed, *head_img;
     const bf16 *cos_tab, *sin_tab;
     int max_pos;
     DevBuf llm_ws, kv, dec_ws, state, seg_ints;
@@ -73,7 +73,8 @@ struct PadtHandle {
     int use_graph = 1;
     int decode_impl = 1;             // 1 = persistent kernel (decode_mega.cu) when it fits, 0 = per-layer kernels (decode.cu)
     int n_sms = 0;
-    DevBuf llm_dev, gbar;
+    DevBuf llm_dev, gbar, stage_tab, stage_off;
+    bool stage_tab_ready = false;
     cudaGraphExec_t step_graph = nullptr;
     int graph_kernels = 0;
     cudaStream_t own_stream = nullptr;

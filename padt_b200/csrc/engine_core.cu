@@ -90,6 +90,16 @@ int engine_build_weights(PadtHandle* h) {
     for (int i = 0; i < d.n_layers; ++i) { o_qkv[i] = take((size_t)qkv_n * D); o_bqkv[i] = take(qkv_n); o_gu[i] = take((size_t)2 * I * D); }
     size_t o_dmlp2[3];
     for (int b = 0; b < 3; ++b) o_dmlp2[b] = take((size_t)Hd * Idp);
+    // stage images for the persistent decode kernel (decode_mega.cu)
+    const int attn_n = d.n_heads * hd;
+    std::vector<size_t> o_iqkv(d.n_layers), o_io(d.n_layers), o_igu(d.n_layers), o_idown(d.n_layers);
+    for (int i = 0; i < d.n_layers; ++i) {
+        o_iqkv[i] = take(decode_mega_image_elems(qkv_n, D));
+        o_io[i] = take(decode_mega_image_elems(D, attn_n));
+        o_igu[i] = take(decode_mega_image_elems(2 * I, D));
+        o_idown[i] = take(decode_mega_image_elems(D, I));
+    }
+    size_t o_ihead = take(decode_mega_image_elems(d.vocab, D));
     RC(h->arena.ensure(need));
     PADT_CHECK_CUDA(cudaMemset(h->arena.p, 0, need));
     uint8_t* base = h->arena.as<uint8_t>();
@@ -138,10 +148,17 @@ int engine_build_weights(PadtHandle* h) {
         RC(launch_interleave_rows(W(p + "mlp.gate_proj.weight"), W(p + "mlp.up_proj.weight"), at(o_gu[i]), I, D, st));
         l.wgu = at(o_gu[i]);
         l.wdown = W(p + "mlp.down_proj.weight");
+        RC(launch_pack_stage_image(l.wqkv, qkv_n, D, at(o_iqkv[i]), st));
+        RC(launch_pack_stage_image(l.wo, D, attn_n, at(o_io[i]), st));
+        RC(launch_pack_stage_image(l.wgu, 2 * I, D, at(o_igu[i]), st));
+        RC(launch_pack_stage_image(l.wdown, D, I, at(o_idown[i]), st));
+        l.iqkv = at(o_iqkv[i]); l.io = at(o_io[i]); l.igu = at(o_igu[i]); l.idown = at(o_idown[i]);
     }
     h->final_norm = W("model.norm.weight");
     h->embed = W("model.embed_tokens.weight");
     h->head = d.tie_word_embeddings ? h->embed : W("lm_head.weight");
+    RC(launch_pack_stage_image(h->head, d.vocab, D, at(o_ihead), st));
+    h->head_img = at(o_ihead);
     // ---- PaDT decoder
     std::string q = "vl_decoder.";
     h->dec_vp_emb = W(q + "vp_embedding.weight"); h->dec_tokens3 = W(q + "bbox_score_mask_tokens.weight");
@@ -225,7 +242,7 @@ extern "C" int padt_destroy(PadtHandle* h) {
     if (h->own_stream) { cudaStreamDestroy(h->own_stream); cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_out); }
     for (auto& kv : h->vit_plans) { kv.second->ints.release(); delete kv.second; }
     for (DevBuf* b : {&h->arena, &h->vit_ws, &h->proto_ws, &h->llm_ws, &h->kv, &h->dec_ws, &h->state, &h->seg_ints, &h->eos_dev, &h->dec_dws,
-                      &h->dec_ints, &h->llm_dev, &h->gbar})
+                      &h->dec_ints, &h->llm_dev, &h->gbar, &h->stage_tab, &h->stage_off})
         b->release();
     delete h;
     return 0;

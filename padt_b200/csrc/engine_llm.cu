@@ -12,6 +12,8 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     p.vocab = d.vocab; p.n_protos = n_protos; p.s_max = h->s_max; p.eps = d.rms_eps;
     p.layers = h->llm.data();
     p.final_norm = h->final_norm; p.head = h->head; p.embed = h->embed; p.protos = (const bf16*)prototypes;
+    p.head_img = h->head_img;
+    p.nseg_d = decode_mega_nseg(d.D); p.nseg_a = decode_mega_nseg(d.n_heads * h->hd); p.nseg_i = decode_mega_nseg(d.I);
     p.cos_tab = h->cos_tab; p.sin_tab = h->sin_tab; p.max_pos = h->max_pos;
     {   // split-KV factor: enough (row, kv head, split) items to cover the SMs, capped at 64 partials per head
         int ns = h->n_sms / (B * d.n_kv_heads);
@@ -52,8 +54,20 @@ int run_step(PadtHandle* h, cudaStream_t st) {
     if (h->decode_impl == 1) {
         int sb, ns, xb;
         size_t smem;
-        if (decode_mega_plan(h->dp, &sb, &ns, &xb, &smem) == 0)
-            return launch_decode_mega(h->dp, h->llm_dev.as<DecodeLayerW>(), h->gbar.as<unsigned int>(), h->n_sms, st);
+        if (decode_mega_plan(h->dp, &sb, &ns, &xb, &smem) == 0) {
+            if (!h->stage_tab_ready) {   // the weight schedule never changes: flatten it once
+                std::vector<uint64_t> tab;
+                std::vector<int> off;
+                RC(decode_mega_build_table(h->dp, h->llm.data(), h->n_sms, tab, off));
+                RC(h->stage_tab.ensure(tab.size() * 8 + 16));
+                RC(h->stage_off.ensure(off.size() * 4));
+                PADT_CHECK_CUDA(cudaMemcpy(h->stage_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+                PADT_CHECK_CUDA(cudaMemcpy(h->stage_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+                h->stage_tab_ready = true;
+            }
+            return launch_decode_mega(h->dp, h->llm_dev.as<DecodeLayerW>(), h->stage_tab.p, h->stage_off.as<int>(), h->gbar.as<unsigned int>(),
+                                      h->n_sms, st);
+        }
     }
     RC(launch_sample_embed(h->dp, st));
     RC(launch_decode_layers(h->dp, st));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <vector>
 
 typedef __nv_bfloat16 bf16;
 
@@ -55,6 +56,9 @@ int launch_sigmoid(bf16* x, long long n, cudaStream_t st);
 // ------------------------------------------------------------------ decode step (decode.cu)
 struct DecodeLayerW {
     const bf16 *ln1, *wqkv, *bqkv, *wo, *ln2, *wgu, *wdown;
+    // "stage images" of the same matrices for the persistent decode kernel: [row group of 8][K segment][8 rows][Kseg + 8 pad],
+    // i.e. exactly the padded shared-memory picture of one ring stage, so a stage is ONE contiguous TMA bulk copy
+    const bf16 *iqkv, *io, *igu, *idown;
 };
 // Device state block (ints): [0]=tokens sampled so far, [1]=rows still unfinished, [2]=padded prompt length L, [3]=reserved,
 // then five per-row arrays of PADT_STATE_BMAX ints: kv_start, rope_delta, vrt_lo, vrt_hi, unfinished.
@@ -66,6 +70,8 @@ struct DecodeParams {
     float eps;
     const DecodeLayerW* layers;   // host array [n_layers]
     const bf16 *final_norm, *head, *embed, *protos;
+    const bf16 *head_img;          // stage image of the head rows (persistent kernel)
+    int nseg_d, nseg_a, nseg_i;    // K segments per row for K = D, nh*hd, I (fixed at pack time)
     const bf16 *cos_tab, *sin_tab; int max_pos;
     bf16 *kcache, *vcache;        // [layers][B][nkv][s_max][hd]
     bf16 *h, *qkv, *act;          // [B,D], [B,(nh+2nkv)hd], [B,max(I, nh*hd)]
@@ -87,4 +93,10 @@ int launch_final_logits(const DecodeParams& p, cudaStream_t st);
 int launch_decode_layers(const DecodeParams& p, cudaStream_t st);
 // persistent one-launch-per-token kernel (decode_mega.cu)
 int decode_mega_plan(const DecodeParams& p, int* slot_bytes, int* n_slots, int* x_bytes, size_t* smem_bytes);
-int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, unsigned int* gbar, int n_sms, cudaStream_t st);
+// stage-image packing (host side of the persistent kernel's weight layout)
+int decode_mega_nseg(int K);
+size_t decode_mega_image_elems(int n_rows, int K);
+int launch_pack_stage_image(const bf16* W, int n_rows, int K, bf16* out, cudaStream_t st);
+int decode_mega_build_table(const DecodeParams& p, const DecodeLayerW* layers_host, int G, std::vector<uint64_t>& tab, std::vector<int>& off);
+int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, const void* stage_tab, const int* stage_off, unsigned int* gbar,
+                       int n_sms, cudaStream_t st);
