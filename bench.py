@@ -224,7 +224,7 @@ def run_ours(args):
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_step")
-    roofline = {"bound": "hbm", "kernel": "decode step (all kernels of one token, CUDA-graph replay)", "achieved": round(achieved, 1),
+    roofline = {"bound": "hbm", "kernel": "decode_mega_kernel (persistent decode step: one launch per token, CUDA-graph replay)", "achieved": round(achieved, 1),
                 "peak": peaks["hbm_gbs"], "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
                 "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic, "bytes_per_step": bytes_step,
                 "ms_per_decode_step": round(step_ms, 4), "decode_tokens_per_s": round(1e3 / step_ms, 1)}
