@@ -252,6 +252,7 @@ extern "C" int padt_set_option(PadtHandle* h, const char* name, int value) {
     PADT_REQUIRE(h && name, "null");
     std::string n(name);
     if (n == "use_graph") { h->use_graph = value; return 0; }
+    if (n == "gemm_tc") { g_padt_gemm_tc = value; return 0; }
     if (n == "decode_impl") {
         h->decode_impl = value;
         if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }

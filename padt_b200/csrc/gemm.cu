@@ -163,8 +163,12 @@ int launch_t(const GemmParams& p, cudaStream_t st) {
 
 }  // namespace
 
+int g_padt_gemm_tc = 1;
+
 int launch_gemm(int epi, const GemmParams& p, cudaStream_t st) {
     if (p.M == 0 || p.N == 0) return 0;
+    if (g_padt_gemm_tc && gemm_tc_eligible(p) && (epi != EPI_SWIGLU || (p.N % 2) == 0) && (epi != EPI_RESID || p.resid != nullptr))
+        return launch_gemm_tc(epi, p, st);
     PADT_REQUIRE(p.K > 0, "K");
     PADT_REQUIRE((p.lda % 8) == 0 && (p.ldw % 8) == 0, "lda/ldw must be multiples of 8 elements (16-byte rows)");
     PADT_REQUIRE((((uintptr_t)p.A) & 15) == 0 && (((uintptr_t)p.W) & 15) == 0, "A/W must be 16-byte aligned");

@@ -1,0 +1,262 @@
+// tcgen05 + TMA dense projection for the large-M stages (ViT blocks / merger, LLM prefill, PaDT-decoder memory side):
+//   C[M,N] = A[M,K] * W[N,K]^T (+bias) with the same fused epilogues and HF rounding points as gemm.cu.
+//
+// One CTA computes a 128 x BN (BN = 256 or 128) tile: a TMA producer thread streams 64-column K panels of A and W
+// (cp.async.bulk.tensor, 128-byte swizzle) through a 4-stage shared-memory ring, one elected thread issues
+// tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) into a TMEM accumulator (BN fp32 columns), tcgen05.commit
+// releases the ring slots, and four epilogue warps read the accumulator back with tcgen05.ld (one TMEM lane = one output
+// row per thread), apply bias / GELU / residual / interleaved SwiGLU and store bf16 rows.
+// Replaces the cuBLAS calls behind every nn.Linear of the reference's tensor-core-bound stages.
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels.h"
+
+#define RC_RET(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+namespace {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), LBO unused (= 1)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(const void* smem) {
+    uint64_t addr = (uint64_t)(smem_u32(smem) & 0x3FFFF) >> 4;
+    return addr | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct TcSmem {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
+    static constexpr int B_BYTES = BN * TC_BK * 2;             // 32 / 16 KB
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));   // SW128 needs 1024-byte tiles
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TcSmem<BN>::STAGE);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* tmem_full = empty + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    const int nk = (p.K + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&full[i], 1); tc_mbar_init(&empty[i], 1); }
+        tc_mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {   // TMEM: BN fp32 accumulator columns for 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---- TMA producer
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % TC_STAGES;
+                tc_mbar_wait(&empty[s], ((kb / TC_STAGES) & 1) ^ 1);
+                tc_mbar_expect_tx(&full[s], TcSmem<BN>::STAGE);
+                uint8_t* sa = smem + s * TcSmem<BN>::STAGE;
+                tma_load_2d(sa, &map_a, kb * TC_BK, m0, &full[s]);
+                tma_load_2d(sa + TcSmem<BN>::A_BYTES, &map_w, kb * TC_BK, n0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---- MMA issuer
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % TC_STAGES;
+                tc_mbar_wait(&full[s], (kb / TC_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint8_t* sa = smem + s * TcSmem<BN>::STAGE;
+                const uint64_t adesc = umma_desc_k_sw128(sa), bdesc = umma_desc_k_sw128(sa + TcSmem<BN>::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)   // advance 16 elements = 32 bytes inside the swizzled row: +2 in the address field
+                    umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&empty[s]);                // frees the slot when these MMAs have read it
+            }
+            umma_commit(tmem_full);                    // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); lane = output row inside the tile
+        tc_mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        const int orow = row_ok ? (p.out_row_map ? p.out_row_map[row] : row) : 0;
+        for (int cb = 0; cb < BN; cb += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, r);
+            const int col0 = n0 + cb;
+            if (!row_ok || col0 >= p.N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(r[j]);
+                int col = col0 + j;
+                if (p.bias && col < p.N) x += bf2f(p.bias[col]);
+                v[j] = rbf(x);
+            }
+            if (EPI == EPI_SWIGLU) {
+                bf16* dst = p.C + (size_t)orow * p.ldc + (col0 >> 1);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2)
+                    if (col0 + j + 1 < p.N) dst[j >> 1] = f2bf(rbf(silu_f(v[j])) * v[j + 1]);
+            } else {
+                if (EPI == EPI_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = rbf(gelu_erf_f(v[j]));
+                }
+                if (EPI == EPI_RESID) {
+                    const bf16* rs = p.resid + (size_t)orow * p.ldr + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) v[j] = rbf(bf2f(rs[j]) + v[j]);
+                }
+                bf16* dst = p.C + (size_t)orow * p.ldc + col0;
+                if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8)
+                        *reinterpret_cast<uint4*>(dst + j) = make_uint4(f2_to_bf2x(v[j], v[j + 1]), f2_to_bf2x(v[j + 2], v[j + 3]),
+                                                                        f2_to_bf2x(v[j + 4], v[j + 5]), f2_to_bf2x(v[j + 6], v[j + 7]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) dst[j] = f2bf(v[j]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap* map, const bf16* base, int rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    PADT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PADT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (rc " + std::to_string((int)r) + ")");
+    return 0;
+}
+
+template <int BN, int EPI>
+int launch_bn(const GemmParams& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
+        configured = true;
+    }
+    CUtensorMap ma, mw;
+    RC_RET(make_map(&ma, p.A, p.M, p.K, p.lda, TC_BM));
+    RC_RET(make_map(&mw, p.W, p.N, p.K, p.ldw, BN));
+    dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
+    gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, st>>>(ma, mw, p);
+    PADT_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int EPI>
+int launch_epi(const GemmParams& p, cudaStream_t st) {
+    if (p.N >= 256) return launch_bn<256, EPI>(p, st);
+    return launch_bn<128, EPI>(p, st);
+}
+
+}  // namespace
+
+// Shapes the tcgen05 path takes; everything else (small M / N / K, odd strides) stays on the mma.sync kernel.
+bool gemm_tc_eligible(const GemmParams& p) {
+    return p.M >= 256 && p.N >= 128 && p.K >= 64 && (p.lda % 8) == 0 && (p.ldw % 8) == 0 && (((uintptr_t)p.A) & 15) == 0 &&
+           (((uintptr_t)p.W) & 15) == 0 && get_encode() != nullptr;
+}
+
+int launch_gemm_tc(int epi, const GemmParams& p, cudaStream_t st) {
+    switch (epi) {
+        case EPI_NONE: return launch_epi<EPI_NONE>(p, st);
+        case EPI_GELU: return launch_epi<EPI_GELU>(p, st);
+        case EPI_RESID: return launch_epi<EPI_RESID>(p, st);
+        case EPI_SWIGLU: return launch_epi<EPI_SWIGLU>(p, st);
+    }
+    padt_set_error("launch_gemm_tc: unknown epilogue");
+    return -1;
+}
