@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) sample_embed_kernel(SampleArgs a) {
 
 __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(DecAttnArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    decode_attn_body(a, blockIdx.x, blockIdx.y, blockIdx.z, smem_raw, threadIdx.x, DA_THREADS, BlockSync());
+    decode_attn_body<true>(a, blockIdx.x, blockIdx.y, blockIdx.z, smem_raw, threadIdx.x, DA_THREADS, BlockSync());
 }
 
 template <int NB, int PRO, int EPI>

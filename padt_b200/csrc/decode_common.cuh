@@ -145,9 +145,44 @@ struct DecAttnArgs {
     float scale_log2;
 };
 
-template <class Sync>
+// key range [k_begin, k_end) of one (row, split) item; `cur` = cache slot of the key appended in this step
+__device__ __forceinline__ void decode_attn_range(const DecAttnArgs& a, int split, int b, int& k_begin, int& k_end, int& cur) {
+    const int s = a.state[0] - 1;            // index of the token being fed
+    cur = a.state[2] + s;
+    const int ks = a.state[st_kvstart(b)];
+    const int n_keys = cur + 1 - ks;
+    int chunk = (n_keys + a.n_split - 1) / a.n_split;
+    chunk = (chunk + 31) & ~31;
+    k_begin = ks + split * chunk;
+    k_end = k_begin + chunk;
+    k_end = k_end > cur + 1 ? cur + 1 : k_end;
+}
+
+// cp.async one K/V tile (keys t0 .. t0+63 of the item) into the padded shared-memory tiles; the key of the current step is
+// not in the cache yet and is zero-filled (its owner writes it from the fresh projection).  Commits one cp.async group.
+__device__ __forceinline__ void decode_attn_issue_tile(const DecAttnArgs& a, int kvh, int b, int t0, int k_end, int cur, uint8_t* smem_raw, int tid,
+                                                       int nthreads) {
+    bf16* sK = reinterpret_cast<bf16*>(smem_raw);
+    bf16* sV = sK + DA_TILE * DA_LD;
+    const bf16* kc = a.kcache + ((size_t)b * a.nkv + kvh) * a.s_max * DA_HD;
+    const bf16* vc = a.vcache + ((size_t)b * a.nkv + kvh) * a.s_max * DA_HD;
+    for (int id = tid; id < DA_TILE * 16; id += nthreads) {
+        int r = id >> 4, c = id & 15;
+        int key = t0 + r;
+        bool ok = key < k_end && key != cur;
+        cp_async16(sK + r * DA_LD + c * 8, kc + (size_t)(ok ? key : 0) * DA_HD + c * 8, ok ? 16 : 0);
+        cp_async16(sV + r * DA_LD + c * 8, vc + (size_t)(ok ? key : 0) * DA_HD + c * 8, ok ? 16 : 0);
+    }
+    cp_async_commit();
+}
+
+// `first_tile_in_flight`: the caller already issued decode_attn_issue_tile for the item's first tile (the persistent kernel
+// does so before the grid barrier that publishes q/k/v, so the cache rows are in shared memory when the barrier opens).
+// COMBINE = true: the last-arriving CTA of a (row, kv head) combines all split partials (per-layer kernel path);
+// COMBINE = false: return after the partial (m, l, acc) of this split is written -- the caller combines (persistent kernel).
+template <bool COMBINE, class Sync>
 __device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split, int kvh, int b, uint8_t* smem_raw, int tid, int nthreads,
-                                                 Sync sync) {
+                                                 Sync sync, bool first_tile_in_flight = false) {
     bf16* sK = reinterpret_cast<bf16*>(smem_raw);           // [64][136]
     bf16* sV = sK + DA_TILE * DA_LD;                        // [64][136]
     float* sQ = reinterpret_cast<float*>(sV + DA_TILE * DA_LD);  // [group][128]
@@ -187,14 +222,7 @@ __device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t0 = k_begin; t0 < k_end; t0 += DA_TILE) {
         sync();   // previous tile fully consumed (also orders the sQ writes on the first pass)
-        for (int id = tid; id < DA_TILE * 16; id += nthreads) {
-            int r = id >> 4, c = id & 15;
-            int key = t0 + r;
-            bool ok = key < k_end && key != cur;
-            cp_async16(sK + r * DA_LD + c * 8, kc + (size_t)(ok ? key : 0) * DA_HD + c * 8, ok ? 16 : 0);
-            cp_async16(sV + r * DA_LD + c * 8, vc + (size_t)(ok ? key : 0) * DA_HD + c * 8, ok ? 16 : 0);
-        }
-        cp_async_commit();
+        if (!(first_tile_in_flight && t0 == k_begin)) decode_attn_issue_tile(a, kvh, b, t0, k_end, cur, smem_raw, tid, nthreads);
         cp_async_wait<0>();
         sync();
         if (owns_new && cur >= t0 && cur < t0 + DA_TILE) {
@@ -265,6 +293,7 @@ __device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split
         *reinterpret_cast<float4*>(a.part_o + base * DA_HD + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         if (lane == 0) { a.part_ml[base * 2] = m_run; a.part_ml[base * 2 + 1] = l_run; }
     }
+    if (!COMBINE) return;
     __threadfence();
     sync();
     if (tid == 0) {

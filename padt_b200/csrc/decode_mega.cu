@@ -25,11 +25,14 @@ namespace {
 constexpr int MK_CW = 16;                     // consumer (tensor-core) warps
 constexpr int MK_CTHREADS = MK_CW * 32;
 constexpr int MK_STHREADS = MK_CTHREADS + 32; // + 1 epilogue warp: the threads that take part in phase-level barriers
-constexpr int MK_THREADS = MK_STHREADS + 32;  // + 1 producer warp
+constexpr int MK_THREADS = MK_STHREADS + 64;  // + 1 producer warp + 1 L2 prefetch warp
 constexpr int MK_NRED = 4;                    // reduction buffers in flight between the consumer warps and the epilogue warp
 constexpr int MK_MAXSLOTS = 24;
 constexpr int MK_GROUP = 8;                   // weight rows per stage (= n of the mma)
 constexpr int MK_MAXGROUPS = 8;               // row groups of one CTA in the small-matrix phases (bias / residual preload)
+constexpr int MK_DEFAULT_PF = 0;               // defaults of PADT_MEGA_PF / PADT_MEGA_FLAGS (see MegaArgs)
+constexpr int MK_DEFAULT_FLAGS = 1 | 4;          // MF_EVICT_FIRST | MF_KV_SMEM
+constexpr int MK_DEFAULT_PF_PACE = 0;
 constexpr int MK_ATTN_SMEM = 2 * DA_TILE * DA_LD * 2 + DA_MAXG * DA_HD * 4 + DA_MAXG * DA_TILE * 4;
 
 struct StageDesc;
@@ -40,8 +43,15 @@ struct MegaArgs {
     int slot_bytes, n_slots, x_bytes, x_ld;
     const struct StageDesc* stage_tab;   // [sum stages] descriptors, CTA c owns [stage_off[c], stage_off[c+1])
     const int* stage_off;
-    int dbg;                      // PADT_MEGA_TIMELINE bits: 1 print cycle breakdown, 2 no compute, 4 no grid barrier, 8 no attention
+    int dbg;                      // PADT_MEGA_TIMELINE bits: 1 print cycle breakdown, 2 no compute, 4 no grid barrier, 8 no attention,
+                                  //   16 per-phase timeline of layer `trace_layer`
+    int pf_depth;                 // L2 prefetch warp: stages kept in flight towards L2 beyond the ring (0 = off)
+    int flags;                    // MF_* bits
+    int trace_layer;
+    int pf_pace;                  // minimum cycles between two stage prefetches (keeps the request queues short during a stall)
+    int attn_off;                 // byte offset of the attention scratch inside the activation region
 };
+enum { MF_EVICT_FIRST = 1, MF_NO_AREG = 2, MF_KV_SMEM = 4, MF_PF_LINES = 8 };
 
 using CSync = NamedSync<1, MK_STHREADS>;
 
@@ -72,6 +82,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     unsigned int v;
@@ -105,8 +125,8 @@ __host__ __device__ inline int pick_nseg(int K, int slot_bytes) {
 __device__ __forceinline__ Seg make_seg(const bf16* W, const bf16* img, int nseg_packed, int row_begin, int n_rows, int K, int cta, int G,
                                          int slot_bytes) {
     Seg s;
-    int groups = (n_rows + MK_GROUP - 1) / MK_GROUP;
-    int lo = (int)(((long long)groups * cta) / G), hi = (int)(((long long)groups * (cta + 1)) / G);
+    const unsigned int groups = (unsigned int)(n_rows + MK_GROUP - 1) / MK_GROUP;       // groups * G < 2^31 for every matrix here
+    const int lo = (int)((groups * (unsigned int)cta) / (unsigned int)G), hi = (int)((groups * (unsigned int)(cta + 1)) / (unsigned int)G);
     int r_lo = lo * MK_GROUP, r_hi = hi * MK_GROUP;
     r_hi = r_hi > n_rows ? n_rows : r_hi;
     s.groups = hi - lo;
@@ -155,19 +175,28 @@ struct StageDesc {
     uint32_t pad;
 };
 
-__device__ void producer_loop(const MegaArgs& a, uint8_t* ring, uint64_t* full, uint64_t* empty, int cta, int G, int lane) {
+__device__ void producer_loop(const MegaArgs& a, uint8_t* ring, uint64_t* full, uint64_t* empty, int cta, int G, int lane,
+                              volatile unsigned int* prog, long long* t_wait_empty) {
     const StageDesc* tab = a.stage_tab + a.stage_off[cta];
     const int n = a.stage_off[cta + 1] - a.stage_off[cta];
     const int ns = a.n_slots;
     if (lane < ns) {
         uint8_t* dst = ring + (size_t)lane * a.slot_bytes;
         uint32_t parity = 0;
+        const bool hint = (a.flags & MF_EVICT_FIRST) != 0;
+        const uint64_t pol = l2_policy_evict_first();
+        long long tw = 0;
         for (int i = lane; i < n; i += ns, parity ^= 1) {
             StageDesc d = tab[i];
+            long long tq = (a.dbg & 1) ? clock64() : 0;
             mbar_wait(&empty[lane], parity ^ 1);
+            if (a.dbg & 1) tw += clock64() - tq;
             mbar_expect_tx(&full[lane], d.bytes);
-            tma_bulk_g2s(dst, d.src, d.bytes, &full[lane]);
+            if (hint) tma_bulk_g2s_hint(dst, d.src, d.bytes, &full[lane], pol);
+            else tma_bulk_g2s(dst, d.src, d.bytes, &full[lane]);
+            if (lane == 0) *prog = (unsigned int)i;     // issue frontier, read by the L2 prefetch warp
         }
+        if (lane == 0) { *prog = (unsigned int)n; *t_wait_empty = tw; }
     }
     __syncwarp();
     if (lane != 0) return;
@@ -194,83 +223,161 @@ __device__ void producer_loop(const MegaArgs& a, uint8_t* ring, uint64_t* full, 
     }
 }
 
+// ---------------------------------------------------------------- L2 prefetch warp
+// The ring holds ~3.6 us of HBM stream; a phase boundary (grid barrier + activation staging, or the attention phase) stalls the
+// consumers for longer than that, and a full ring stops the producer, so HBM would sit idle.  This warp keeps the stream
+// going during such stalls: it walks the same descriptor table `pf_depth` stages ahead of the producer's issue frontier and
+// asks the L2 (126 MB) to fetch those stages; when the consumers resume, the ring refills at L2 rather than HBM rate.
+__device__ void prefetch_loop(const MegaArgs& a, int cta, int lane, volatile unsigned int* prog) {
+    const StageDesc* tab = a.stage_tab + a.stage_off[cta];
+    const int n = a.stage_off[cta + 1] - a.stage_off[cta];
+    const int depth = a.pf_depth;
+    if (depth <= 0) return;
+    int pf = a.n_slots;                          // the first ring fill is issued by the producer itself
+    while (pf < n) {
+        int lim = (int)*prog + a.n_slots + depth;
+        lim = lim > n ? n : lim;
+        if (pf >= lim) { __nanosleep(64); continue; }
+        if (a.pf_pace > 0) lim = pf + 1;        // paced: one stage at a time
+        if (a.flags & MF_PF_LINES) {
+            for (int i = pf; i < lim; ++i) {
+                StageDesc d = tab[i];
+                const char* src = reinterpret_cast<const char*>(d.src);
+                for (uint32_t o = (uint32_t)lane * 128; o < d.bytes; o += 32 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o) : "memory");
+            }
+        } else {
+            for (int i = pf + lane; i < lim; i += 32) {
+                StageDesc d = tab[i];
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(d.src), "r"(d.bytes) : "memory");
+            }
+        }
+        pf = lim;
+        if (a.pf_pace > 0) {
+            long long t = clock64();
+            while (clock64() - t < a.pf_pace) __nanosleep(32);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- consumer helpers
+// Shared-memory operations on 32-bit shared-window addresses: the addresses are computed once per phase, so the inner loops
+// carry no generic->shared conversions or index arithmetic (the v3 loop spent ~35 instructions per two k-steps on them and was
+// ISSUE bound at ~700 cycles per 16 KB stage, i.e. no faster than HBM delivers a stage).
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void ldsm_x4_s(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_s(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t lds32_s(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// D += A * B with A = {a0, 0, a2, 0}: only the first 8 rows of the 16-row A tile (the batch rows) are populated
+__device__ __forceinline__ void mma_rows8(float* c, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%5}, {%7,%8}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
+}
+
 // Grid barrier over the consumer threads of all CTAs.  bar.sync orders this CTA's writes before thread 0's gpu-scope
 // release-increment (cumulativity); the acquire poll + bar.sync publishes the other CTAs' writes to every thread.
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& target, int G, int tid, int dbg = 0) {
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& target, int G, int tid, int dbg) {
     CSync()();
     if (dbg & 4) return;
     target += (unsigned int)G;
     if (tid == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-        while (ld_acquire_u32(bar) < target) __nanosleep(32);
+        while (ld_acquire_u32(bar) < target) {}
     }
     CSync()();
 }
 
-// activation rows -> shared memory, row stride x_ld elements (K + 8: the 16-byte pad keeps the A-fragment loads conflict free)
-__device__ __forceinline__ void stage_x_plain(const bf16* x, int K, int B, bf16* xs, int x_ld, int tid) {
+// activation rows -> shared memory, row stride K + 8 elements (the 16-byte pad keeps the A-fragment loads conflict free).
+// ln_w != null: RMSNorm prologue, bit-identical to rmsnorm_kernel / the decode.cu prologue (rms_rstd_warp + rms_apply8).
+__device__ __forceinline__ void stage_x(const bf16* src, const bf16* ln_w, float eps, int K, int B, bf16* xs, int tid, int lane, bf16* copy0,
+                                        bf16* copy1) {
     if (tid >= MK_CTHREADS) return;
-    for (int b = 0; b < B; ++b)
-        for (int c = tid * 8; c < K; c += MK_CTHREADS * 8)
-            *reinterpret_cast<uint4*>(xs + (size_t)b * x_ld + c) = *reinterpret_cast<const uint4*>(x + (size_t)b * K + c);
-}
-
-// RMSNorm prologue, bit-identical to rmsnorm_kernel / the decode.cu prologue (rms_rstd_warp + rms_apply8)
-__device__ __forceinline__ void stage_x_rmsnorm(const bf16* h, const bf16* w, float eps, int K, int B, bf16* xs, int x_ld, int tid, int lane,
-                                                bf16* copy0, bf16* copy1) {
-    if (tid >= MK_CTHREADS) return;
+    const int x_ld = K + 8;
     for (int b = 0; b < B; ++b) {
-        const bf16* xr = h + (size_t)b * K;
-        float rstd = rms_rstd_warp(xr, K, eps, lane);
-        for (int c = tid * 8; c < K; c += MK_CTHREADS * 8) {
-            uint4 o = rms_apply8(*reinterpret_cast<const uint4*>(xr + c), *reinterpret_cast<const uint4*>(w + c), rstd);
-            *reinterpret_cast<uint4*>(xs + (size_t)b * x_ld + c) = o;
-            if (copy0) *reinterpret_cast<uint4*>(copy0 + (size_t)b * K + c) = o;
-            if (copy1) *reinterpret_cast<uint4*>(copy1 + (size_t)b * K + c) = o;
+        const bf16* xr = src + (size_t)b * K;
+        if (ln_w) {
+            float rstd = rms_rstd_warp(xr, K, eps, lane);
+            for (int c = tid * 8; c < K; c += MK_CTHREADS * 8) {
+                uint4 o = rms_apply8(*reinterpret_cast<const uint4*>(xr + c), *reinterpret_cast<const uint4*>(ln_w + c), rstd);
+                *reinterpret_cast<uint4*>(xs + (size_t)b * x_ld + c) = o;
+                if (copy0) *reinterpret_cast<uint4*>(copy0 + (size_t)b * K + c) = o;
+                if (copy1) *reinterpret_cast<uint4*>(copy1 + (size_t)b * K + c) = o;
+            }
+        } else {
+            for (int c = tid * 8; c < K; c += MK_CTHREADS * 8)
+                *reinterpret_cast<uint4*>(xs + (size_t)b * x_ld + c) = *reinterpret_cast<const uint4*>(xr + c);
         }
     }
 }
 
 enum { EP_BIAS = 0, EP_RESID = 1, EP_SWIGLU = 2, EP_LOGITS = 3 };
 
-struct Scratch {
+struct SmemMap {                 // 32-bit shared-window addresses / pointers of the fixed regions
+    uint32_t ring, full, empty, red_full, red_empty, xs;
     float* red;                  // [MK_NRED][MK_CW][B][8] partial sums (K slices of the 16 consumer warps)
-    uint64_t *red_full, *red_empty;
     float* pre;                  // [8 batch][MK_MAXGROUPS*8] preloaded bias / residual values (epilogue warp only)
 };
 
+struct ArgMax { float v[2]; int i[2]; int lo[2], hi[2]; };   // epilogue-warp state: lane -> batch rows (lane/8) and 4 + (lane/8)
+
 // Consume one segment from the ring; `it` / `grp` are CTA-wide stage / row-group counters every thread advances identically.
 // Consumer warps (0..15): two half-CTAs of 8 warps alternate over the stages (even / odd K segment); inside a stage every warp
-// multiplies its own k16-steps (ldmatrix + mma.sync, two independent accumulator chains).  After the last stage of a row group
-// a warp drops its 8 partial sums into a reduction buffer and signals an mbarrier -- it never waits for the other warps.
-// Epilogue warp (16): waits for the 16 partials of a group, adds them in warp order and applies the HF epilogue.
-template <int EP>
-__device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, const uint8_t* ring, uint64_t* full, uint64_t* empty, uint32_t& it,
-                                            uint32_t& grp, const bf16* xs, int tid, const bf16* bias, bf16* y, int n_out, const Scratch& sc,
-                                            float* best_v, int* best_i, const int* vlo, const int* vhi, long long& t_full) {
+// multiplies its own k16-steps (ldmatrix + mma.sync, two independent accumulator chains).  A warp always owns the SAME K slice
+// of a segment, so when the segment has <= 2 K segments and 64 k-steps (K = 2048: q/k/v, o_proj, gate/up, LM head) its
+// activation fragments are loaded into 16 registers ONCE per phase and the per-stage loop is 4 x (ldmatrix.x4 + 2 mma).
+// After the last stage of a row group a warp drops its 8 partial sums into a reduction buffer and signals an mbarrier -- it
+// never waits for the other warps.  Epilogue warp (16): waits for the 16 partials of a group, adds them in warp order and
+// applies the HF epilogue.
+__device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int ep, const SmemMap& sm, uint32_t& it, uint32_t& grp, int tid,
+                                            const bf16* bias, bf16* y, int n_out, ArgMax& am) {
     const DecodeParams& p = a.p;
     const int warp = tid >> 5, lane = tid & 31;
     const int B = p.B;
+    const int n_slots = a.n_slots;
+    uint32_t slot = it % (uint32_t)n_slots, parity = (it / (uint32_t)n_slots) & 1u;
+    it += (uint32_t)s.groups * s.nseg;
+    uint32_t g_idx = grp;
+    grp += (uint32_t)s.groups;
     if (warp == MK_CW) {
         // ================= epilogue warp: lane -> (batch row eb = pass*4 + lane/8, weight row en = lane%8)
         const int en = lane & 7;
-        if (EP == EP_BIAS || EP == EP_RESID) {   // preload so that the per-group epilogue never waits on global memory
+        if (ep == EP_BIAS || ep == EP_RESID) {   // preload so that the per-group epilogue never waits on global memory
             for (int pass = 0; pass * 4 < B; ++pass) {
                 int eb = pass * 4 + (lane >> 3);
                 if (eb < B)
                     for (int gi = 0; gi < s.groups && gi < MK_MAXGROUPS; ++gi) {
                         int r = gi * 8 + en;
                         if (r < s.rows)
-                            sc.pre[eb * (MK_MAXGROUPS * 8) + r] = EP == EP_BIAS ? (bias ? bf2f(bias[s.row_lo + r]) : 0.f) : bf2f(y[(size_t)eb * n_out + s.row_lo + r]);
+                            sm.pre[eb * (MK_MAXGROUPS * 8) + r] = ep == EP_BIAS ? (bias ? bf2f(bias[s.row_lo + r]) : 0.f) : bf2f(y[(size_t)eb * n_out + s.row_lo + r]);
                     }
             }
             __syncwarp();
         }
-        for (int gi = 0; gi < s.groups; ++gi, ++grp) {
-            const int buf = grp % MK_NRED;
-            mbar_wait(&sc.red_full[buf], (grp / MK_NRED) & 1);
-            const float* red = sc.red + (size_t)buf * MK_CW * B * 8;
+        for (int gi = 0; gi < s.groups; ++gi, ++g_idx) {
+            const uint32_t buf = g_idx % MK_NRED;
+            mbar_wait_s(sm.red_full + buf * 8, (g_idx / MK_NRED) & 1);
+            const float* red = sm.red + (size_t)buf * MK_CW * B * 8;
             const int r = gi * 8 + en;
             if (r < s.rows && !(a.dbg & 2)) {
                 const int n = s.row_lo + r;
@@ -280,11 +387,11 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, con
                     float sum = 0.f;
 #pragma unroll
                     for (int w = 0; w < MK_CW; ++w) sum += red[(w * B + eb) * 8 + en];
-                    if (EP == EP_BIAS) {
-                        y[(size_t)eb * n_out + n] = f2bf(sum + sc.pre[eb * (MK_MAXGROUPS * 8) + r]);
-                    } else if (EP == EP_RESID) {
-                        y[(size_t)eb * n_out + n] = f2bf(sc.pre[eb * (MK_MAXGROUPS * 8) + r] + rbf(sum));
-                    } else if (EP == EP_SWIGLU) {
+                    if (ep == EP_BIAS) {
+                        y[(size_t)eb * n_out + n] = f2bf(sum + sm.pre[eb * (MK_MAXGROUPS * 8) + r]);
+                    } else if (ep == EP_RESID) {
+                        y[(size_t)eb * n_out + n] = f2bf(sm.pre[eb * (MK_MAXGROUPS * 8) + r] + rbf(sum));
+                    } else if (ep == EP_SWIGLU) {
                         if ((en & 1) == 0) {   // even row = gate_j, odd row = up_j of the interleaved weight
                             float up = 0.f;
 #pragma unroll
@@ -294,15 +401,14 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, con
                         }
                     } else {   // EP_LOGITS: bf16-rounded logit, -inf outside the row's own VRT range, first max wins
                         float l0 = rbf(sum);
-                        bool ok = n < p.vocab || (n - p.vocab >= vlo[pass] && n - p.vocab < vhi[pass]);
-                        if (ok && (l0 > best_v[pass] || (l0 == best_v[pass] && n < best_i[pass]))) { best_v[pass] = l0; best_i[pass] = n; }
+                        bool ok = n < p.vocab || (n - p.vocab >= am.lo[pass] && n - p.vocab < am.hi[pass]);
+                        if (ok && (l0 > am.v[pass] || (l0 == am.v[pass] && n < am.i[pass]))) { am.v[pass] = l0; am.i[pass] = n; }
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sc.red_empty[buf]);
+            if (lane == 0) mbar_arrive_s(sm.red_empty + buf * 8);
         }
-        it += (uint32_t)s.groups * s.nseg;
         return;
     }
     // ================= consumer warps
@@ -311,68 +417,126 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, con
     const int set = warp >> 3, wi = warp & 7;
     const int ksteps = s.Kseg >> 4;
     const int k0 = (ksteps * wi) / 8, k1 = (ksteps * (wi + 1)) / 8;
-    for (int gi = 0; gi < s.groups; ++gi, ++grp) {
+    const bool live = g < B;
+    // per-lane byte offset of the ldmatrix.x4 rows inside a stage: matrices 0/1 = k-step kk (k 0-7 / 8-15), 2/3 = k-step kk+1
+    const uint32_t w_off = (uint32_t)(lane & 7) * row_stride + (uint32_t)(((lane >> 4) * 16 + ((lane >> 3) & 1) * 8) * 2) + (uint32_t)k0 * 32u;
+    const uint32_t x_row = sm.xs + (uint32_t)((g * (s.K + 8) + 2 * t + k0 * 16) * 2);
+    const bool reg_path = s.nseg <= 2 && ksteps == 64 && !(a.flags & MF_NO_AREG);
+    uint32_t areg[16];
+    if (reg_path) {
+        // this warp's activation fragments: K segment `set` (segment 0 when there is only one), k-steps [8 wi, 8 wi + 8)
+        const uint32_t xb = x_row + (uint32_t)((s.nseg == 2 ? set : 0) * s.Kseg * 2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            areg[2 * i] = live ? lds32_s(xb + i * 32) : 0u;
+            areg[2 * i + 1] = live ? lds32_s(xb + i * 32 + 16) : 0u;
+        }
+    }
+    const bool skip_math = (a.dbg & (2 | 64)) != 0;
+    for (int gi = 0; gi < s.groups; ++gi, ++g_idx) {
         float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int sg = 0; sg < s.nseg; ++sg, ++it) {
-            if ((sg & 1) != set && s.nseg > 1) continue;          // the other half owns this stage
-            if (s.nseg == 1 && set != 0) continue;
-            const int slot = it % a.n_slots;
-            const uint32_t parity = (it / a.n_slots) & 1;
-            mbar_wait(&full[slot], parity);
-            if (!(a.dbg & (2 | 64))) {
-                const uint8_t* sb = ring + (size_t)slot * a.slot_bytes;
-                const bf16* xrow = xs + (size_t)g * a.x_ld + (size_t)sg * s.Kseg + 2 * t;
-                int kk = k0;
-#pragma unroll 2
-                for (; kk + 1 < k1; kk += 2) {
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4(b0, b1, b2, b3, sb + (lane & 7) * row_stride + ((kk + (lane >> 4)) * 16 + ((lane >> 3) & 1) * 8) * 2);
-                    uint32_t a0 = 0, a2 = 0, a4 = 0, a6 = 0;
-                    if (g < B) {
-                        a0 = *reinterpret_cast<const uint32_t*>(xrow + kk * 16);
-                        a2 = *reinterpret_cast<const uint32_t*>(xrow + kk * 16 + 8);
-                        a4 = *reinterpret_cast<const uint32_t*>(xrow + kk * 16 + 16);
-                        a6 = *reinterpret_cast<const uint32_t*>(xrow + kk * 16 + 24);
+        for (int sg = 0; sg < s.nseg; ++sg) {
+            const uint32_t my_slot = slot, my_parity = parity;
+            if (++slot == (uint32_t)n_slots) { slot = 0; parity ^= 1u; }
+            if (s.nseg > 1 ? ((sg & 1) != set) : (set != 0)) continue;          // the other half owns this stage
+            mbar_wait_s(sm.full + my_slot * 8, my_parity);
+            if (!skip_math) {
+                const uint32_t wb = sm.ring + my_slot * (uint32_t)a.slot_bytes + w_off;
+                if (reg_path) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4_s(b0, b1, b2, b3, wb + j * 64);
+                        mma_rows8(c, areg[4 * j], areg[4 * j + 1], b0, b1);      // two independent accumulator chains
+                        mma_rows8(c2, areg[4 * j + 2], areg[4 * j + 3], b2, b3);
                     }
-                    uint32_t fa[4] = {a0, 0u, a2, 0u}, fb[4] = {a4, 0u, a6, 0u};
-                    mma_bf16_16816(c, fa, b0, b1);      // two independent accumulator chains
-                    mma_bf16_16816(c2, fb, b2, b3);
-                }
-                if (kk < k1) {
-                    uint32_t b0, b1;
-                    ldmatrix_x2(b0, b1, sb + (lane & 7) * row_stride + (kk * 16 + ((lane >> 3) & 1) * 8) * 2);
-                    uint32_t a0 = 0, a2 = 0;
-                    if (g < B) {
-                        a0 = *reinterpret_cast<const uint32_t*>(xrow + kk * 16);
-                        a2 = *reinterpret_cast<const uint32_t*>(xrow + kk * 16 + 8);
+                } else {
+                    uint32_t wa = wb, xa = x_row + (uint32_t)(sg * s.Kseg * 2);
+                    int kk = k0;
+                    for (; kk + 1 < k1; kk += 2, wa += 64, xa += 64) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4_s(b0, b1, b2, b3, wa);
+                        uint32_t a0 = 0, a2 = 0, a4 = 0, a6 = 0;
+                        if (live) { a0 = lds32_s(xa); a2 = lds32_s(xa + 16); a4 = lds32_s(xa + 32); a6 = lds32_s(xa + 48); }
+                        mma_rows8(c, a0, a2, b0, b1);
+                        mma_rows8(c2, a4, a6, b2, b3);
                     }
-                    uint32_t fa[4] = {a0, 0u, a2, 0u};
-                    mma_bf16_16816(c, fa, b0, b1);
+                    if (kk < k1) {
+                        uint32_t b0, b1;
+                        ldsm_x2_s(b0, b1, wa - (uint32_t)((lane >> 4) * 32));    // x2 uses lanes 0-15 only: drop the k-step kk+1 offset
+                        uint32_t a0 = 0, a2 = 0;
+                        if (live) { a0 = lds32_s(xa); a2 = lds32_s(xa + 16); }
+                        mma_rows8(c, a0, a2, b0, b1);
+                    }
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
+            if (lane == 0) mbar_arrive_s(sm.empty + my_slot * 8);
         }
-        float r0 = c[0] + c2[0], r1 = c[1] + c2[1];
+        const float r0 = c[0] + c2[0], r1 = c[1] + c2[1];
         // hand the K-slice partial of this row group to the epilogue warp
-        const int buf = grp % MK_NRED;
-        mbar_wait(&sc.red_empty[buf], ((grp / MK_NRED) & 1) ^ 1);
-        if (g < B) {
-            float* red = sc.red + ((size_t)(buf * MK_CW + warp) * B + g) * 8;
+        const uint32_t buf = g_idx % MK_NRED;
+        mbar_wait_s(sm.red_empty + buf * 8, ((g_idx / MK_NRED) & 1) ^ 1);
+        if (live) {
+            float* red = sm.red + ((size_t)(buf * MK_CW + warp) * B + g) * 8;
             red[2 * t] = r0;
             red[2 * t + 1] = r1;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sc.red_full[buf]);
+        if (lane == 0) mbar_arrive_s(sm.red_full + buf * 8);
     }
-    (void)t_full;
 }
 
+// Distributed combine of the split-KV partials of one (row, kv head): the n_split CTAs that produced the partials each reduce
+// a slice of the group*128 output values over ALL splits (one warp per 4 values, lanes over splits), instead of the last-arriving
+// CTA reducing everything serially (that serial tail was ~5 us per layer on the critical path of every CTA).
+__device__ __forceinline__ void attn_merge_slice(const DecodeParams& p, int b, int kvh, int split, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int group = p.nh / p.nkv;
+    const int total = group * DA_HD;                                  // values of this kv head's query heads
+    int per = (total + p.n_split - 1) / p.n_split;
+    per = (per + 3) & ~3;
+    const int e_lo = split * per, e_hi = (e_lo + per) < total ? (e_lo + per) : total;
+    for (int e0 = e_lo + warp * 4; e0 < e_hi; e0 += (MK_STHREADS / 32) * 4) {
+        const int head = kvh * group + e0 / DA_HD, dim = e0 % DA_HD;
+        const size_t base = ((size_t)b * p.nh + head) * p.n_split;
+        float M = -INFINITY;
+        float mj[3], lj[3];
+        float4 oj[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                                  // n_split <= 96 here (launch checks <= 64)
+            int j = lane + 32 * k;
+            bool ok = j < p.n_split;
+            mj[k] = ok ? __ldcg(p.part_ml + (base + j) * 2) : -INFINITY;
+            lj[k] = ok ? __ldcg(p.part_ml + (base + j) * 2 + 1) : 0.f;
+            oj[k] = ok ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (base + j) * DA_HD + dim)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            M = fmaxf(M, mj[k]);
+        }
+        M = warp_max(M);
+        float L = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float w = (mj[k] == -INFINITY) ? 0.f : exp2f(mj[k] - M);
+            L += lj[k] * w;
+            o0 += oj[k].x * w; o1 += oj[k].y * w; o2 += oj[k].z * w; o3 += oj[k].w * w;
+        }
+        L = warp_sum(L); o0 = warp_sum(o0); o1 = warp_sum(o1); o2 = warp_sum(o2); o3 = warp_sum(o3);
+        if (lane == 0) {
+            float inv = L > 0.f ? 1.0f / L : 0.f;
+            uint2 pk;
+            pk.x = f2_to_bf2x(o0 * inv, o1 * inv);
+            pk.y = f2_to_bf2x(o2 * inv, o3 * inv);
+            *reinterpret_cast<uint2*>(p.act + (size_t)b * p.nh * DA_HD + (size_t)head * DA_HD + dim) = pk;
+        }
+    }
+}
+
+template <bool TL>
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DecodeParams& p = a.p;
     uint8_t* ring = smem;
-    uint8_t* xa = ring + (size_t)a.n_slots * a.slot_bytes;    // activation rows, aliased with the attention scratch
+    uint8_t* xa = ring + (size_t)a.n_slots * a.slot_bytes;    // activation rows; the attention scratch sits at xa + attn_off
     bf16* xs = reinterpret_cast<bf16*>(xa);
     uint64_t* full = reinterpret_cast<uint64_t*>(xa + a.x_bytes);
     uint64_t* empty = full + MK_MAXSLOTS;
@@ -382,37 +546,45 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     __shared__ float s_pre[8 * MK_MAXGROUPS * 8];
     __shared__ float s_bv[64];
     __shared__ int s_bi[64];
+    __shared__ volatile unsigned int s_prog;
+    __shared__ long long s_prod_wait;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
 
     if (tid == 0) {
+        s_prog = 0; s_prod_wait = 0;
         for (int i = 0; i < a.n_slots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MK_CW / 2); }   // half the warps consume a stage
         for (int i = 0; i < MK_NRED; ++i) { mbar_init(&red_full[i], MK_CW); mbar_init(&red_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (warp == MK_CW + 1) {   // producer warp: streams this CTA's weight schedule for the whole step
-        producer_loop(a, ring, full, empty, cta, G, lane);
+        producer_loop(a, ring, full, empty, cta, G, lane, &s_prog, &s_prod_wait);
+        return;
+    }
+    if (warp == MK_CW + 2) {   // L2 prefetch warp
+        prefetch_loop(a, cta, lane, &s_prog);
         return;
     }
 
-    Scratch sc;
-    sc.red = red; sc.red_full = red_full; sc.red_empty = red_empty;
-    sc.pre = s_pre;
+    SmemMap sm;
+    sm.ring = smem_u32(ring); sm.full = smem_u32(full); sm.empty = smem_u32(empty);
+    sm.red_full = smem_u32(red_full); sm.red_empty = smem_u32(red_empty); sm.xs = smem_u32(xs);
+    sm.red = red; sm.pre = s_pre;
     unsigned int target = 0;
     uint32_t it = 0, grp = 0;
-    // arg-max state lives in the epilogue warp: lane -> batch rows (lane/8) and 4 + (lane/8)
-    float best_v[2] = {-INFINITY, -INFINITY};
-    int best_i[2] = {0x7fffffff, 0x7fffffff};
-    int vlo[2], vhi[2];
+    ArgMax am;
     for (int k = 0; k < 2; ++k) {
         int eb = k * 4 + (lane >> 3);
-        vlo[k] = eb < p.B ? p.dev_state[st_vlo(eb)] : 0;
-        vhi[k] = eb < p.B ? p.dev_state[st_vhi(eb)] : 0;
+        am.v[k] = -INFINITY; am.i[k] = 0x7fffffff;
+        am.lo[k] = eb < p.B ? p.dev_state[st_vlo(eb)] : 0;
+        am.hi[k] = eb < p.B ? p.dev_state[st_vhi(eb)] : 0;
     }
-    long long t_bar = 0, t_cons = 0, t_stage = 0, t_attn = 0, t_full = 0, t0 = clock64(), tt;
-#define TSTART() tt = clock64()
-#define TADD(acc) acc += clock64() - tt
+    // cycle accounting (PADT_MEGA_TIMELINE & 1): per phase kind [qkv | attention | o_proj | gate-up | down | logits]
+    long long t_bar[6] = {0, 0, 0, 0, 0, 0}, t_work[6] = {0, 0, 0, 0, 0, 0}, t_stage[6] = {0, 0, 0, 0, 0, 0};
+    long long t0 = TL ? clock64() : 0, tt = 0;
+#define TSTART() do { if (TL) tt = clock64(); } while (0)
+#define TADD(acc) do { if (TL) acc += clock64() - tt; } while (0)
 
     // ---- phase 0: sample the token predicted by the previous forward, log it, gather its embedding row(s) into h
     if (cta == 0) {
@@ -424,124 +596,125 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         sa.embed = p.embed; sa.protos = p.protos; sa.h = p.h;
         sample_embed_body(sa, tid, MK_STHREADS, CSync());
     }
-    TSTART(); grid_sync(a.gbar, target, G, tid, a.dbg); TADD(t_bar);
-    const long long t_sample = clock64() - t0;
+    grid_sync(a.gbar, target, G, tid, a.dbg);
+    const long long t_sample = TL ? clock64() - t0 : 0;
 
     const int qkv_n = (p.nh + 2 * p.nkv) * p.hd;
     const size_t layer_kv = (size_t)p.B * p.nkv * p.s_max * p.hd;
-    for (int li = 0; li < p.n_layers; ++li) {
-        const DecodeLayerW w = a.layers[li];
-        // warm L2 with the K/V rows this CTA will attend over after the next barrier (they were written in earlier steps)
-        if (tid == 0 && !(a.dbg & 8)) {
-            const int items = p.n_split * p.nkv * p.B;
-            for (int item = cta; item < items; item += G) {
-                int split = item % p.n_split, kvh = (item / p.n_split) % p.nkv, b = item / (p.n_split * p.nkv);
-                int cur = p.dev_state[2] + p.dev_state[0] - 1, ks = p.dev_state[st_kvstart(b)];
-                int n_keys = cur + 1 - ks;
-                int chunk = ((n_keys + p.n_split - 1) / p.n_split + 31) & ~31;
-                int kb = ks + split * chunk, ke = kb + chunk;
-                ke = ke > cur ? cur : ke;            // the new key is not in the cache yet
-                if (ke > kb) {
-                    size_t off = (((size_t)li * p.B + b) * p.nkv + kvh) * p.s_max * p.hd + (size_t)kb * p.hd;
-                    uint32_t bytes = (uint32_t)(ke - kb) * p.hd * 2;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.kcache + off), "r"(bytes) : "memory");
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.vcache + off), "r"(bytes) : "memory");
-                }
+    uint8_t* attn_smem = xa + a.attn_off;
+    // this CTA's attention item (n_split * nkv * B <= grid size: at most one item per CTA)
+    const bool has_item = cta < p.n_split * p.nkv * p.B && !(a.dbg & 8);
+    const int a_split = cta % p.n_split, a_kvh = (cta / p.n_split) % p.nkv, a_b = cta / (p.n_split * p.nkv);
+    DecAttnArgs da;
+    da.qkv = p.qkv; da.cos_tab = p.cos_tab; da.sin_tab = p.sin_tab; da.max_pos = p.max_pos; da.sec0 = 0; da.sec1 = 0;
+    da.state = p.dev_state; da.part_o = p.part_o; da.part_ml = p.part_ml; da.counters = p.attn_counters;
+    da.out = p.act; da.B = p.B; da.nh = p.nh; da.nkv = p.nkv; da.s_max = p.s_max; da.n_split = p.n_split;
+    da.scale_log2 = rsqrtf((float)p.hd) * 1.4426950408889634f;
+    int a_kb = 0, a_ke = 0, a_cur = 0;
+    if (has_item) decode_attn_range(da, a_split, a_b, a_kb, a_ke, a_cur);   // state[0] was advanced by the sample phase of THIS launch
+    const unsigned int step_idx = (unsigned int)(p.dev_state[0] - 1);       // decode launches since the prefill
+    int plo = 0, phi = 0;
+    proto_range(p, plo, phi);
+
+    // ---- ONE phase loop (a single copy of the staging / consume / barrier code): 5 phases per layer, then head rows, then
+    //      the prototype rows of the request
+    const int n_phase = p.n_layers * 5 + 2;
+    DecodeLayerW w = a.layers[0];
+    bool kv_in_flight = false;
+    for (int ph = 0; ph < n_phase; ++ph) {
+        const int li = ph / 5, k = ph < p.n_layers * 5 ? ph % 5 : 5 + (ph - p.n_layers * 5);   // k: 0..4 layer phases, 5 head, 6 prototypes
+        if (k == 0) {
+            w = a.layers[li];
+            da.kcache = p.kcache + li * layer_kv; da.vcache = p.vcache + li * layer_kv;
+            kv_in_flight = false;
+            if (has_item && a_ke > a_kb && (a.flags & MF_KV_SMEM)) {
+                // the cache rows of earlier steps do not depend on this step: pull the item's first K/V tile into shared memory
+                // now, so that it is resident when the barrier after the q/k/v projection opens
+                decode_attn_issue_tile(da, a_kvh, a_b, a_kb, a_ke, a_cur, attn_smem, tid, MK_STHREADS);
+                kv_in_flight = true;
             }
         }
-        // (1) RMSNorm -> q/k/v projection + bias
-        TSTART();
-        stage_x_rmsnorm(p.h, w.ln1, p.eps, p.D, p.B, xs, a.x_ld, tid, lane, nullptr, nullptr);
-        CSync()();
-        TADD(t_stage); TSTART();
-        consume_seg<EP_BIAS>(a, layer_seg(a, w, SEG_QKV, cta, G), ring, full, empty, it, grp, xs, tid, w.bqkv, p.qkv, qkv_n, sc, best_v, best_i, vlo,
-                             vhi, t_full);
-        TADD(t_cons); TSTART();
-        grid_sync(a.gbar, target, G, tid, a.dbg);
-        TADD(t_bar); TSTART();
-        // (2) M-RoPE + KV append + split-KV attention (+ combine by the last CTA of each (row, kv head))
-        {
-            DecAttnArgs da;
-            da.qkv = p.qkv; da.kcache = p.kcache + li * layer_kv; da.vcache = p.vcache + li * layer_kv;
-            da.cos_tab = p.cos_tab; da.sin_tab = p.sin_tab; da.max_pos = p.max_pos; da.sec0 = 0; da.sec1 = 0;
-            da.state = p.dev_state; da.part_o = p.part_o; da.part_ml = p.part_ml; da.counters = p.attn_counters;
-            da.out = p.act; da.B = p.B; da.nh = p.nh; da.nkv = p.nkv; da.s_max = p.s_max; da.n_split = p.n_split;
-            da.scale_log2 = rsqrtf((float)p.hd) * 1.4426950408889634f;
-            const int items = p.n_split * p.nkv * p.B;
-            for (int item = cta; item < items && !(a.dbg & 8); item += G) {
-                int split = item % p.n_split, kvh = (item / p.n_split) % p.nkv, b = item / (p.n_split * p.nkv);
-                decode_attn_body(da, split, kvh, b, xa, tid, MK_STHREADS, CSync());
+        if (k == 1) {
+            // ---- M-RoPE + KV append + split-KV attention; the n_split CTAs of a (row, kv head) then combine slices of the result
+            TSTART();
+            if (has_item) {
+                decode_attn_body<false>(da, a_split, a_kvh, a_b, attn_smem, tid, MK_STHREADS, CSync(), kv_in_flight);
+                __threadfence();
                 CSync()();
+                if (tid == 0) {
+                    unsigned int* cnt = reinterpret_cast<unsigned int*>(p.attn_counters) + p.B * p.nkv + a_b * p.nkv + a_kvh;   // monotonic counters
+                    const unsigned int want = (step_idx * (unsigned int)p.n_layers + (unsigned int)li + 1u) * (unsigned int)p.n_split;
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+                    while (ld_acquire_u32(cnt) < want) {}
+                }
+                CSync()();
+                attn_merge_slice(p, a_b, a_kvh, a_split, tid);
             }
+            TADD(t_work[1]); TSTART();
+            grid_sync(a.gbar, target, G, tid, a.dbg);
+            TADD(t_bar[1]);
+            continue;
         }
-        TADD(t_attn); TSTART();
-        grid_sync(a.gbar, target, G, tid, a.dbg);
-        TADD(t_bar); TSTART();
-        // (3) o_proj + residual
-        stage_x_plain(p.act, p.nh * p.hd, p.B, xs, a.x_ld, tid);
-        CSync()();
-        TADD(t_stage); TSTART();
-        consume_seg<EP_RESID>(a, layer_seg(a, w, SEG_O, cta, G), ring, full, empty, it, grp, xs, tid, nullptr, p.h, p.D, sc, best_v, best_i, vlo, vhi,
-                              t_full);
-        TADD(t_cons); TSTART();
-        grid_sync(a.gbar, target, G, tid, a.dbg);
-        TADD(t_bar); TSTART();
-        // (4) RMSNorm -> gate/up -> SiLU*up
-        stage_x_rmsnorm(p.h, w.ln2, p.eps, p.D, p.B, xs, a.x_ld, tid, lane, nullptr, nullptr);
-        CSync()();
-        TADD(t_stage); TSTART();
-        consume_seg<EP_SWIGLU>(a, layer_seg(a, w, SEG_GU, cta, G), ring, full, empty, it, grp, xs, tid, nullptr, p.act, p.I, sc, best_v, best_i, vlo,
-                               vhi, t_full);
-        TADD(t_cons); TSTART();
-        grid_sync(a.gbar, target, G, tid, a.dbg);
-        TADD(t_bar); TSTART();
-        // (5) down_proj + residual
-        stage_x_plain(p.act, p.I, p.B, xs, a.x_ld, tid);
-        CSync()();
-        TADD(t_stage); TSTART();
-        consume_seg<EP_RESID>(a, layer_seg(a, w, SEG_DOWN, cta, G), ring, full, empty, it, grp, xs, tid, nullptr, p.h, p.D, sc, best_v, best_i, vlo,
-                              vhi, t_full);
-        TADD(t_cons); TSTART();
-        grid_sync(a.gbar, target, G, tid, a.dbg);
-        TADD(t_bar);
+        // ---- projection phases
+        Seg s;
+        const bf16 *src, *ln = nullptr, *bias = nullptr;
+        bf16 *y = nullptr, *copy0 = nullptr, *copy1 = nullptr;
+        int K, ep, n_out = 0;
+        bool stage = true;
+        switch (k) {
+            case 0: s = layer_seg(a, w, SEG_QKV, cta, G); src = p.h; ln = w.ln1; K = p.D; ep = EP_BIAS; bias = w.bqkv; y = p.qkv; n_out = qkv_n; break;
+            case 2: s = layer_seg(a, w, SEG_O, cta, G); src = p.act; K = p.nh * p.hd; ep = EP_RESID; y = p.h; n_out = p.D; break;
+            case 3: s = layer_seg(a, w, SEG_GU, cta, G); src = p.h; ln = w.ln2; K = p.D; ep = EP_SWIGLU; y = p.act; n_out = p.I; break;
+            case 4: s = layer_seg(a, w, SEG_DOWN, cta, G); src = p.act; K = p.I; ep = EP_RESID; y = p.h; n_out = p.D; break;
+            case 5:
+                s = make_seg(p.head, p.head_img, p.nseg_d, 0, p.vocab, p.D, cta, G, a.slot_bytes);
+                src = p.h; ln = p.final_norm; K = p.D; ep = EP_LOGITS;
+                if (cta == 0) {
+                    copy0 = p.last_hidden;
+                    const int t = p.dev_state[0];
+                    if (p.hidden_steps && t < p.max_steps) copy1 = p.hidden_steps + (size_t)t * p.B * p.D;
+                }
+                break;
+            default:
+                if (phi <= plo) continue;
+                s = make_seg(p.protos + (size_t)plo * p.D, nullptr, 0, p.vocab + plo, phi - plo, p.D, cta, G, a.slot_bytes);
+                src = p.h; K = p.D; ep = EP_LOGITS; stage = false;      // the normalised rows are still staged
+                break;
+        }
+        const int tk = k < 5 ? k : 5;
+        TSTART();
+        if (stage) {
+            stage_x(src, ln, p.eps, K, p.B, xs, tid, lane, copy0, copy1);
+            CSync()();
+        }
+        TADD(t_stage[tk]); TSTART();
+        consume_seg(a, s, ep, sm, it, grp, tid, bias, y, n_out, am);
+        TADD(t_work[tk]); TSTART();
+        if (k < 5) grid_sync(a.gbar, target, G, tid, a.dbg);
+        TADD(t_bar[tk]);
     }
-    const long long t_layers = clock64() - t0;
-    // ---- final norm + VRT-extended logits + masked arg-max partial of this CTA
-    {
-        bf16* log = nullptr;
-        if (cta == 0 && p.hidden_steps) {
-            int t = p.dev_state[0];
-            if (t < p.max_steps) log = p.hidden_steps + (size_t)t * p.B * p.D;
-        }
-        stage_x_rmsnorm(p.h, p.final_norm, p.eps, p.D, p.B, xs, a.x_ld, tid, lane, cta == 0 ? p.last_hidden : nullptr, log);
-        CSync()();
-        consume_seg<EP_LOGITS>(a, make_seg(p.head, p.head_img, p.nseg_d, 0, p.vocab, p.D, cta, G, a.slot_bytes), ring, full, empty, it, grp, xs, tid, nullptr, nullptr, 0, sc,
-                               best_v, best_i, vlo, vhi, t_full);
-        int plo, phi;
-        proto_range(p, plo, phi);
-        if (phi > plo)
-            consume_seg<EP_LOGITS>(a, make_seg(p.protos + (size_t)plo * p.D, nullptr, 0, p.vocab + plo, phi - plo, p.D, cta, G, a.slot_bytes), ring, full,
-                                   empty,
-                                   it, grp, xs, tid, nullptr, nullptr, 0, sc, best_v, best_i, vlo, vhi, t_full);
-        if (warp == MK_CW) {   // epilogue warp publishes its per-lane maxima: entry [batch row][weight-row lane]
-            s_bv[lane] = best_v[0]; s_bi[lane] = best_i[0];
-            s_bv[32 + lane] = best_v[1]; s_bi[32 + lane] = best_i[1];
-        }
-        CSync()();
-        if (tid < p.B) {
-            float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int k = 0; k < 8; ++k) {
-                float v = s_bv[tid * 8 + k]; int i = s_bi[tid * 8 + k];
-                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-            }
-            p.amax_val[(size_t)cta * p.B + tid] = bv;
-            p.amax_idx[(size_t)cta * p.B + tid] = bi;
-        }
-        if (cta == 0 && tid == 0) p.dev_state[3] = G;
+    // ---- masked arg-max partial of this CTA
+    if (warp == MK_CW) {   // epilogue warp publishes its per-lane maxima: entry [batch row][weight-row lane]
+        s_bv[lane] = am.v[0]; s_bi[lane] = am.i[0];
+        s_bv[32 + lane] = am.v[1]; s_bi[32 + lane] = am.i[1];
     }
-    if ((a.dbg & 1) && tid == 0 && (cta == 0 || cta == G / 2 || cta == G - 1))
-        printf("[mega cta %d] cycles: total %lld | sample+bar %lld | layers-end %lld | grid-barrier wait %lld | consume %lld (of which waiting for TMA data, warp0: %lld) | x staging %lld | attention %lld\n",
-               cta, (long long)(clock64() - t0), t_sample, t_layers, t_bar, t_cons, t_full, t_stage, t_attn);
+    CSync()();
+    if (tid < p.B) {
+        float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int k = 0; k < 8; ++k) {
+            float v = s_bv[tid * 8 + k]; int i = s_bi[tid * 8 + k];
+            if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        p.amax_val[(size_t)cta * p.B + tid] = bv;
+        p.amax_idx[(size_t)cta * p.B + tid] = bi;
+    }
+    if (cta == 0 && tid == 0) p.dev_state[3] = G;
+    if (TL && (a.dbg & 1) && tid == 0 && (cta == 0 || cta == G / 2 || cta == G - 1)) {
+        printf("[mega cta %d] cycles: total %lld | sample+bar %lld\n"
+               "[mega cta %d] per phase (qkv attn o gu down logits): barrier %lld %lld %lld %lld %lld %lld | work %lld %lld %lld %lld %lld %lld | stage %lld %lld %lld %lld %lld %lld\n",
+               cta, (long long)(clock64() - t0), t_sample, cta, t_bar[0], t_bar[1], t_bar[2], t_bar[3], t_bar[4], t_bar[5], t_work[0], t_work[1],
+               t_work[2], t_work[3], t_work[4], t_work[5], t_stage[0], t_stage[1], t_stage[2], t_stage[3], t_stage[4], t_stage[5]);
+    }
 #undef TSTART
 #undef TADD
 }
@@ -583,13 +756,17 @@ int launch_pack_stage_image(const bf16* W, int n_rows, int K, bf16* out, cudaStr
     return 0;
 }
 
+static int decode_mega_attn_off(const DecodeParams& p) { return (p.B * (p.D + 8) * 2 + 127) / 128 * 128; }
+
 // Plans shared memory for the persistent kernel; returns 0 and fills the outputs, or -1 when the model does not fit.
 int decode_mega_plan(const DecodeParams& p, int* slot_bytes, int* n_slots, int* x_bytes, size_t* smem_bytes) {
     if (p.B > 8) return -1;
     int kmax = p.I > p.D ? p.I : p.D;
     kmax = kmax > p.nh * p.hd ? kmax : p.nh * p.hd;
     int xb = p.B * (kmax + 8) * 2;
-    xb = xb > MK_ATTN_SMEM ? xb : MK_ATTN_SMEM;
+    // the attention scratch sits behind the activation rows of the q/k/v phase: its first K/V tile is filled while they are in use
+    const int attn_need = decode_mega_attn_off(p) + MK_ATTN_SMEM;
+    xb = xb > attn_need ? xb : attn_need;
     xb = (xb + 127) / 128 * 128;
     // one slot = 8 rows x Kseg columns (+16 B pad per row); stages of at most 24 KB
     int sb = 0;
@@ -657,6 +834,12 @@ int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, co
     a.p = p; a.layers = layers_dev; a.gbar = gbar;
     a.stage_tab = reinterpret_cast<const StageDesc*>(stage_tab); a.stage_off = stage_off;
     a.dbg = getenv("PADT_MEGA_TIMELINE") ? atoi(getenv("PADT_MEGA_TIMELINE")) : 0;
+    a.pf_depth = getenv("PADT_MEGA_PF") ? atoi(getenv("PADT_MEGA_PF")) : MK_DEFAULT_PF;
+    a.flags = getenv("PADT_MEGA_FLAGS") ? atoi(getenv("PADT_MEGA_FLAGS")) : MK_DEFAULT_FLAGS;
+    a.trace_layer = getenv("PADT_MEGA_TRACE_LAYER") ? atoi(getenv("PADT_MEGA_TRACE_LAYER")) : 10;
+    a.pf_pace = getenv("PADT_MEGA_PF_PACE") ? atoi(getenv("PADT_MEGA_PF_PACE")) : MK_DEFAULT_PF_PACE;
+    a.attn_off = decode_mega_attn_off(p);
+    PADT_REQUIRE(p.n_split * p.nkv * p.B <= n_sms, "one attention item per CTA");
     size_t smem;
     if (decode_mega_plan(p, &a.slot_bytes, &a.n_slots, &a.x_bytes, &smem)) {
         padt_set_error("persistent decode kernel: configuration does not fit in shared memory");
@@ -672,12 +855,14 @@ int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, co
     PADT_REQUIRE(((uintptr_t)p.head & 15) == 0 && (p.protos == nullptr || ((uintptr_t)p.protos & 15) == 0), "TMA bulk copies need 16-byte aligned rows");
     static size_t configured = 0;
     if (smem > configured) {
-        PADT_CHECK_CUDA(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PADT_CHECK_CUDA(cudaFuncSetAttribute(decode_mega_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PADT_CHECK_CUDA(cudaFuncSetAttribute(decode_mega_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     PADT_CHECK_CUDA(cudaMemsetAsync(a.gbar, 0, sizeof(unsigned int), st));
     void* args[] = {(void*)&a};
-    PADT_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_mega_kernel, dim3(n_sms), dim3(MK_THREADS), args, smem, st));
+    const void* fn = a.dbg ? (const void*)decode_mega_kernel<true> : (const void*)decode_mega_kernel<false>;   // <true>: cycle accounting
+    PADT_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(n_sms), dim3(MK_THREADS), args, smem, st));
     ++g_padt_launches;
     return 0;
 }

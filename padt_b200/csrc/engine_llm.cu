@@ -29,7 +29,7 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     size_t o_h = take((size_t)B * d.D * 2), o_qkv = take((size_t)B * qkv_n * 2), o_act = take((size_t)B * act_n * 2);
     size_t o_po = take((size_t)B * d.n_heads * p.n_split * h->hd * 4), o_pml = take((size_t)B * d.n_heads * p.n_split * 2 * 4);
     size_t o_av = take((size_t)p.n_amax_blocks * B * 4), o_ai = take((size_t)p.n_amax_blocks * B * 4);
-    size_t o_cnt = take((size_t)B * d.n_kv_heads * 4), o_tok = take((size_t)B * 8);
+    size_t o_cnt = take((size_t)B * d.n_kv_heads * 4 * 2), o_tok = take((size_t)B * 8);   // [B*nkv] re-armed counters (decode.cu) + [B*nkv] monotonic (decode_mega.cu)
     bool fresh = off > h->dec_ws.bytes;
     RC(h->dec_ws.ensure(off));
     uint8_t* b = h->dec_ws.as<uint8_t>();
@@ -38,7 +38,7 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     p.amax_val = (float*)(b + o_av); p.amax_idx = (int*)(b + o_ai);
     p.attn_counters = (int*)(b + o_cnt); p.cur_token = (long long*)(b + o_tok);
     (void)fresh;
-    PADT_CHECK_CUDA(cudaMemset(p.attn_counters, 0, (size_t)B * d.n_kv_heads * 4));
+    PADT_CHECK_CUDA(cudaMemset(p.attn_counters, 0, (size_t)B * d.n_kv_heads * 4 * 2));
     const size_t layer_kv = (size_t)B * d.n_kv_heads * h->s_max * h->hd;
     p.kcache = h->kv.as<bf16>();
     p.vcache = p.kcache + layer_kv * d.n_layers;
