@@ -30,8 +30,8 @@ constexpr int MK_NRED = 4;                    // reduction buffers in flight bet
 constexpr int MK_MAXSLOTS = 24;
 constexpr int MK_GROUP = 8;                   // weight rows per stage (= n of the mma)
 constexpr int MK_MAXGROUPS = 8;               // row groups of one CTA in the small-matrix phases (bias / residual preload)
-constexpr int MK_DEFAULT_PF = 0;               // defaults of PADT_MEGA_PF / PADT_MEGA_FLAGS (see MegaArgs)
-constexpr int MK_DEFAULT_FLAGS = 1 | 4;          // MF_EVICT_FIRST | MF_KV_SMEM
+constexpr int MK_DEFAULT_PF = 16;               // defaults of PADT_MEGA_PF / PADT_MEGA_FLAGS (see MegaArgs)
+constexpr int MK_DEFAULT_FLAGS = 1 | 4 | 8;      // MF_EVICT_FIRST | MF_KV_SMEM | MF_PF_LINES
 constexpr int MK_DEFAULT_PF_PACE = 0;
 constexpr int MK_ATTN_SMEM = 2 * DA_TILE * DA_LD * 2 + DA_MAXG * DA_HD * 4 + DA_MAXG * DA_TILE * 4;
 
@@ -51,7 +51,7 @@ struct MegaArgs {
     int pf_pace;                  // minimum cycles between two stage prefetches (keeps the request queues short during a stall)
     int attn_off;                 // byte offset of the attention scratch inside the activation region
 };
-enum { MF_EVICT_FIRST = 1, MF_NO_AREG = 2, MF_KV_SMEM = 4, MF_PF_LINES = 8 };
+enum { MF_EVICT_FIRST = 1, MF_NO_AREG = 2, MF_KV_SMEM = 4, MF_PF_LINES = 8, MF_PF_EVICT_LAST = 16, MF_BAR_FLAGS = 32 };
 
 using CSync = NamedSync<1, MK_STHREADS>;
 
@@ -233,24 +233,31 @@ __device__ void prefetch_loop(const MegaArgs& a, int cta, int lane, volatile uns
     const int n = a.stage_off[cta + 1] - a.stage_off[cta];
     const int depth = a.pf_depth;
     if (depth <= 0) return;
+    const bool keep = (a.flags & MF_PF_EVICT_LAST) != 0;
     int pf = a.n_slots;                          // the first ring fill is issued by the producer itself
     while (pf < n) {
         int lim = (int)*prog + a.n_slots + depth;
         lim = lim > n ? n : lim;
         if (pf >= lim) { __nanosleep(64); continue; }
         if (a.pf_pace > 0) lim = pf + 1;        // paced: one stage at a time
+        lim = lim > pf + 32 ? pf + 32 : lim;    // one descriptor per lane per round (a single coalesced load, no serial latency chain)
+        StageDesc mine = {nullptr, 0, 0};
+        if (pf + lane < lim) mine = tab[pf + lane];
         if (a.flags & MF_PF_LINES) {
-            for (int i = pf; i < lim; ++i) {
-                StageDesc d = tab[i];
-                const char* src = reinterpret_cast<const char*>(d.src);
-                for (uint32_t o = (uint32_t)lane * 128; o < d.bytes; o += 32 * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o) : "memory");
+            // through the LSU: one 128-byte line per lane per instruction; keeps the TMA queue free for the ring copies
+            for (int i = 0; i < lim - pf; ++i) {
+                const char* src = reinterpret_cast<const char*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)mine.src, i));
+                const uint32_t bytes = __shfl_sync(0xffffffffu, mine.bytes, i);
+                if (keep) {
+                    for (uint32_t o = (uint32_t)lane * 128; o < bytes; o += 32 * 128)
+                        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(src + o) : "memory");
+                } else {
+                    for (uint32_t o = (uint32_t)lane * 128; o < bytes; o += 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o) : "memory");
+                }
             }
-        } else {
-            for (int i = pf + lane; i < lim; i += 32) {
-                StageDesc d = tab[i];
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(d.src), "r"(d.bytes) : "memory");
-            }
+        } else if (pf + lane < lim) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(mine.src), "r"(mine.bytes) : "memory");
         }
         pf = lim;
         if (a.pf_pace > 0) {
@@ -294,7 +301,6 @@ __device__ __forceinline__ void mma_rows8(float* c, uint32_t a0, uint32_t a2, ui
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
 }
-
 // Grid barrier over the consumer threads of all CTAs.  bar.sync orders this CTA's writes before thread 0's gpu-scope
 // release-increment (cumulativity); the acquire poll + bar.sync publishes the other CTAs' writes to every thread.
 __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& target, int G, int tid, int dbg) {
@@ -317,9 +323,13 @@ __device__ __forceinline__ void stage_x(const bf16* src, const bf16* ln_w, float
     for (int b = 0; b < B; ++b) {
         const bf16* xr = src + (size_t)b * K;
         if (ln_w) {
+            // the norm weights do not depend on the statistics: fetch this thread's first chunk before the reduction, so the
+            // apply pass does not start with a second dependent L2 round trip
+            uint4 w0 = make_uint4(0, 0, 0, 0);
+            if (tid * 8 < K) w0 = *reinterpret_cast<const uint4*>(ln_w + tid * 8);
             float rstd = rms_rstd_warp(xr, K, eps, lane);
             for (int c = tid * 8; c < K; c += MK_CTHREADS * 8) {
-                uint4 o = rms_apply8(*reinterpret_cast<const uint4*>(xr + c), *reinterpret_cast<const uint4*>(ln_w + c), rstd);
+                uint4 o = rms_apply8(*reinterpret_cast<const uint4*>(xr + c), c == tid * 8 ? w0 : *reinterpret_cast<const uint4*>(ln_w + c), rstd);
                 *reinterpret_cast<uint4*>(xs + (size_t)b * x_ld + c) = o;
                 if (copy0) *reinterpret_cast<uint4*>(copy0 + (size_t)b * K + c) = o;
                 if (copy1) *reinterpret_cast<uint4*>(copy1 + (size_t)b * K + c) = o;
@@ -339,7 +349,7 @@ struct SmemMap {                 // 32-bit shared-window addresses / pointers of
     float* pre;                  // [8 batch][MK_MAXGROUPS*8] preloaded bias / residual values (epilogue warp only)
 };
 
-struct ArgMax { float v[2]; int i[2]; int lo[2], hi[2]; };   // epilogue-warp state: lane -> batch rows (lane/8) and 4 + (lane/8)
+struct ArgMax { float v[2][32]; int i[2][32]; int lo[2][32], hi[2][32]; };   // epilogue-warp state in shared memory: [pass][lane] -> batch row pass*4 + lane/8
 
 // Consume one segment from the ring; `it` / `grp` are CTA-wide stage / row-group counters every thread advances identically.
 // Consumer warps (0..15): two half-CTAs of 8 warps alternate over the stages (even / odd K segment); inside a stage every warp
@@ -381,7 +391,8 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
             const int r = gi * 8 + en;
             if (r < s.rows && !(a.dbg & 2)) {
                 const int n = s.row_lo + r;
-                for (int pass = 0; pass * 4 < B; ++pass) {
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {              // static indices keep the arg-max state in registers
                     const int eb = pass * 4 + (lane >> 3);
                     if (eb >= B) break;
                     float sum = 0.f;
@@ -401,8 +412,9 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
                         }
                     } else {   // EP_LOGITS: bf16-rounded logit, -inf outside the row's own VRT range, first max wins
                         float l0 = rbf(sum);
-                        bool ok = n < p.vocab || (n - p.vocab >= am.lo[pass] && n - p.vocab < am.hi[pass]);
-                        if (ok && (l0 > am.v[pass] || (l0 == am.v[pass] && n < am.i[pass]))) { am.v[pass] = l0; am.i[pass] = n; }
+                        bool ok = n < p.vocab || (n - p.vocab >= am.lo[pass][lane] && n - p.vocab < am.hi[pass][lane]);
+                        const float bv = am.v[pass][lane];
+                        if (ok && (l0 > bv || (l0 == bv && n < am.i[pass][lane]))) { am.v[pass][lane] = l0; am.i[pass][lane] = n; }
                     }
                 }
             }
@@ -544,10 +556,10 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     uint64_t* red_empty = red_full + MK_NRED;
     float* red = reinterpret_cast<float*>(red_empty + MK_NRED);          // [MK_NRED][MK_CW][B][8]
     __shared__ float s_pre[8 * MK_MAXGROUPS * 8];
-    __shared__ float s_bv[64];
-    __shared__ int s_bi[64];
     __shared__ volatile unsigned int s_prog;
     __shared__ long long s_prod_wait;
+    __shared__ DecodeLayerW s_w[2];
+    __shared__ ArgMax am;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
 
@@ -573,19 +585,20 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     sm.red = red; sm.pre = s_pre;
     unsigned int target = 0;
     uint32_t it = 0, grp = 0;
-    ArgMax am;
-    for (int k = 0; k < 2; ++k) {
-        int eb = k * 4 + (lane >> 3);
-        am.v[k] = -INFINITY; am.i[k] = 0x7fffffff;
-        am.lo[k] = eb < p.B ? p.dev_state[st_vlo(eb)] : 0;
-        am.hi[k] = eb < p.B ? p.dev_state[st_vhi(eb)] : 0;
-    }
+    if (warp == MK_CW)
+        for (int k = 0; k < 2; ++k) {
+            int eb = k * 4 + (lane >> 3);
+            am.v[k][lane] = -INFINITY; am.i[k][lane] = 0x7fffffff;
+            am.lo[k][lane] = eb < p.B ? p.dev_state[st_vlo(eb)] : 0;
+            am.hi[k][lane] = eb < p.B ? p.dev_state[st_vhi(eb)] : 0;
+        }
     // cycle accounting (PADT_MEGA_TIMELINE & 1): per phase kind [qkv | attention | o_proj | gate-up | down | logits]
     long long t_bar[6] = {0, 0, 0, 0, 0, 0}, t_work[6] = {0, 0, 0, 0, 0, 0}, t_stage[6] = {0, 0, 0, 0, 0, 0};
     long long t0 = TL ? clock64() : 0, tt = 0;
 #define TSTART() do { if (TL) tt = clock64(); } while (0)
 #define TADD(acc) do { if (TL) acc += clock64() - tt; } while (0)
 
+    if (warp == 0 && lane < (int)(sizeof(DecodeLayerW) / 4)) reinterpret_cast<uint32_t*>(&s_w[0])[lane] = reinterpret_cast<const uint32_t*>(&a.layers[0])[lane];
     // ---- phase 0: sample the token predicted by the previous forward, log it, gather its embedding row(s) into h
     if (cta == 0) {
         SampleArgs sa;
@@ -605,13 +618,17 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     // this CTA's attention item (n_split * nkv * B <= grid size: at most one item per CTA)
     const bool has_item = cta < p.n_split * p.nkv * p.B && !(a.dbg & 8);
     const int a_split = cta % p.n_split, a_kvh = (cta / p.n_split) % p.nkv, a_b = cta / (p.n_split * p.nkv);
-    DecAttnArgs da;
-    da.qkv = p.qkv; da.cos_tab = p.cos_tab; da.sin_tab = p.sin_tab; da.max_pos = p.max_pos; da.sec0 = 0; da.sec1 = 0;
-    da.state = p.dev_state; da.part_o = p.part_o; da.part_ml = p.part_ml; da.counters = p.attn_counters;
-    da.out = p.act; da.B = p.B; da.nh = p.nh; da.nkv = p.nkv; da.s_max = p.s_max; da.n_split = p.n_split;
-    da.scale_log2 = rsqrtf((float)p.hd) * 1.4426950408889634f;
+    auto attn_args = [&](int li_) {          // rebuilt where needed: kernel parameters live in constant memory, registers are scarce
+        DecAttnArgs da;
+        da.qkv = p.qkv; da.cos_tab = p.cos_tab; da.sin_tab = p.sin_tab; da.max_pos = p.max_pos; da.sec0 = 0; da.sec1 = 0;
+        da.state = p.dev_state; da.part_o = p.part_o; da.part_ml = p.part_ml; da.counters = p.attn_counters;
+        da.out = p.act; da.B = p.B; da.nh = p.nh; da.nkv = p.nkv; da.s_max = p.s_max; da.n_split = p.n_split;
+        da.scale_log2 = rsqrtf((float)p.hd) * 1.4426950408889634f;
+        da.kcache = p.kcache + li_ * layer_kv; da.vcache = p.vcache + li_ * layer_kv;
+        return da;
+    };
     int a_kb = 0, a_ke = 0, a_cur = 0;
-    if (has_item) decode_attn_range(da, a_split, a_b, a_kb, a_ke, a_cur);   // state[0] was advanced by the sample phase of THIS launch
+    if (has_item) decode_attn_range(attn_args(0), a_split, a_b, a_kb, a_ke, a_cur);   // state[0] was advanced by the sample phase of THIS launch
     const unsigned int step_idx = (unsigned int)(p.dev_state[0] - 1);       // decode launches since the prefill
     int plo = 0, phi = 0;
     proto_range(p, plo, phi);
@@ -619,18 +636,21 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     // ---- ONE phase loop (a single copy of the staging / consume / barrier code): 5 phases per layer, then head rows, then
     //      the prototype rows of the request
     const int n_phase = p.n_layers * 5 + 2;
-    DecodeLayerW w = a.layers[0];
     bool kv_in_flight = false;
+    static_assert(sizeof(DecodeLayerW) % 4 == 0 && sizeof(DecodeLayerW) / 4 <= 32, "layer descriptor is copied by one warp");
     for (int ph = 0; ph < n_phase; ++ph) {
         const int li = ph / 5, k = ph < p.n_layers * 5 ? ph % 5 : 5 + (ph - p.n_layers * 5);   // k: 0..4 layer phases, 5 head, 6 prototypes
+        if (k == 3 && li + 1 < p.n_layers && warp == 0 && lane < (int)(sizeof(DecodeLayerW) / 4))
+            // next layer's descriptor -> shared memory during the long gate/up phase (a global load at the layer start would sit
+            // on the critical path right after a barrier has invalidated L1)
+            reinterpret_cast<uint32_t*>(&s_w[(li + 1) & 1])[lane] = reinterpret_cast<const uint32_t*>(&a.layers[li + 1])[lane];
+        const DecodeLayerW& w = s_w[li & 1];       // fields are read at their point of use (keeps 22 registers free)
         if (k == 0) {
-            w = a.layers[li];
-            da.kcache = p.kcache + li * layer_kv; da.vcache = p.vcache + li * layer_kv;
             kv_in_flight = false;
             if (has_item && a_ke > a_kb && (a.flags & MF_KV_SMEM)) {
                 // the cache rows of earlier steps do not depend on this step: pull the item's first K/V tile into shared memory
                 // now, so that it is resident when the barrier after the q/k/v projection opens
-                decode_attn_issue_tile(da, a_kvh, a_b, a_kb, a_ke, a_cur, attn_smem, tid, MK_STHREADS);
+                decode_attn_issue_tile(attn_args(li), a_kvh, a_b, a_kb, a_ke, a_cur, attn_smem, tid, MK_STHREADS);
                 kv_in_flight = true;
             }
         }
@@ -638,7 +658,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
             // ---- M-RoPE + KV append + split-KV attention; the n_split CTAs of a (row, kv head) then combine slices of the result
             TSTART();
             if (has_item) {
-                decode_attn_body<false>(da, a_split, a_kvh, a_b, attn_smem, tid, MK_STHREADS, CSync(), kv_in_flight);
+                decode_attn_body<false>(attn_args(li), a_split, a_kvh, a_b, attn_smem, tid, MK_STHREADS, CSync(), kv_in_flight);
                 __threadfence();
                 CSync()();
                 if (tid == 0) {
@@ -694,15 +714,11 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         TADD(t_bar[tk]);
     }
     // ---- masked arg-max partial of this CTA
-    if (warp == MK_CW) {   // epilogue warp publishes its per-lane maxima: entry [batch row][weight-row lane]
-        s_bv[lane] = am.v[0]; s_bi[lane] = am.i[0];
-        s_bv[32 + lane] = am.v[1]; s_bi[32 + lane] = am.i[1];
-    }
-    CSync()();
+    CSync()();             // entry [pass][lane]: batch row pass*4 + lane/8, weight-row lane%8
     if (tid < p.B) {
         float bv = -INFINITY; int bi = 0x7fffffff;
         for (int k = 0; k < 8; ++k) {
-            float v = s_bv[tid * 8 + k]; int i = s_bi[tid * 8 + k];
+            float v = am.v[tid >> 2][(tid & 3) * 8 + k]; int i = am.i[tid >> 2][(tid & 3) * 8 + k];
             if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
         }
         p.amax_val[(size_t)cta * p.B + tid] = bv;

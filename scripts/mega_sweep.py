@@ -20,6 +20,7 @@ ap.add_argument("--model", default="PaDT_Pro_3B")
 ap.add_argument("--configs", default="")
 ap.add_argument("--trace", default="")
 ap.add_argument("--out", default="gpurun_out/mega_sweep.jsonl")
+ap.add_argument("--lib", default="", help="load this build of the library instead of padt_b200/libpadt_b200.so (A/B runs)")
 a = ap.parse_args()
 
 DEFAULT = [(0, 0, 0), (0, 2, 0), (0, 4, 0), (0, 6, 0), (0, 7, 0),
@@ -33,6 +34,9 @@ def parse_cfgs(s):
     return [tuple(int(x) for x in c.split(",")) for c in s.split(";") if c.strip()]
 
 
+if a.lib:
+    from padt_b200 import _capi
+    _capi.LIB_PATH = os.path.abspath(a.lib)
 cfgs = parse_cfgs(a.configs) if a.configs else DEFAULT
 cfg = PRESETS[a.model]()
 model = PaDTForConditionalGeneration.from_random(cfg, seed=0, device="cuda:0")
@@ -81,7 +85,7 @@ with open(a.out, "w") as f:
             if ref_toks is None:
                 ref_toks = toks
             same = toks == ref_toks
-        line = {"pf": pf, "flags": flags, "pace": pace, "ms_per_step": round(ms, 4), "all": [round(x, 4) for x in allr],
+        line = {"lib": os.path.basename(a.lib) if a.lib else "tree", "pf": pf, "flags": flags, "pace": pace, "ms_per_step": round(ms, 4), "all": [round(x, 4) for x in allr],
                 "GBps": round(nbytes / ms / 1e6, 1), "frac": round(nbytes / ms / 1e6 / peaks["hbm_gbs"], 4), "tokens_same_as_first": same}
         print(json.dumps(line), flush=True)
         f.write(json.dumps(line) + "\n")
