@@ -8,6 +8,7 @@
 //
 // v1 kernel: mma.sync m16n8k16 tiles fed by a 4-stage cp.async pipeline, 128x128x32 CTA tile, XOR-swizzled smem.
 // (The tcgen05/TMA replacement for the large-M shapes is gemm_tc.cu.)
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -167,6 +168,7 @@ int g_padt_gemm_tc = 1;
 
 int launch_gemm(int epi, const GemmParams& p, cudaStream_t st) {
     if (p.M == 0 || p.N == 0) return 0;
+    if (const char* e = getenv("PADT_GEMM_TC")) g_padt_gemm_tc = atoi(e);   // A/B switch: 0 mma.sync, 1 persistent tcgen05, 2 one-tile tcgen05
     if (g_padt_gemm_tc && gemm_tc_eligible(p) && (epi != EPI_SWIGLU || (p.N % 2) == 0) && (epi != EPI_RESID || p.resid != nullptr))
         return launch_gemm_tc(epi, p, st);
     PADT_REQUIRE(p.K > 0, "K");

@@ -17,6 +17,7 @@ namespace {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
 constexpr int TC_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TC_THREADS_P = 320; // persistent kernel: warps 2-9 = epilogue (two warps per TMEM lane quarter, half of the columns each)
 
 __device__ __forceinline__ void tc_mbar_init(uint64_t* b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
@@ -70,12 +71,89 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Epilogue of one 32-column block of one output row (r = fp32 accumulators read from TMEM): bias / GELU / residual /
+// interleaved SwiGLU with the HF rounding points, 16-byte stores.
+template <int EPI>
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, const uint32_t* r, int orow, int col0) {
+    const bool full = col0 + 32 <= p.N;
+    float v[32];
+    // bias: the 32 columns of this block are the same for every lane -> four broadcast 16-byte loads
+    if (p.bias) {
+        const bf16* bp = p.bias + col0;
+        if (full && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 bv = *reinterpret_cast<const uint4*>(bp + j);
+                float2 b0 = bf2x_to_f2(bv.x), b1 = bf2x_to_f2(bv.y), b2 = bf2x_to_f2(bv.z), b3 = bf2x_to_f2(bv.w);
+                v[j] = b0.x; v[j + 1] = b0.y; v[j + 2] = b1.x; v[j + 3] = b1.y; v[j + 4] = b2.x; v[j + 5] = b2.y; v[j + 6] = b3.x; v[j + 7] = b3.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = col0 + j < p.N ? bf2f(bp[j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = rbf(__uint_as_float(r[j]) + v[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = rbf(__uint_as_float(r[j]));
+    }
+    if (EPI == EPI_SWIGLU) {
+        // interleaved (gate, up) column pairs -> 16 outputs = 32 contiguous bytes per thread: two 16-byte stores
+        // (scalar 2-byte stores from 32 different rows cost 16x the write sectors and dominated this kernel)
+        bf16* dst = p.C + (size_t)orow * p.ldc + (col0 >> 1);
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            o[j >> 2] = f2_to_bf2x(rbf(silu_f(v[j])) * v[j + 1], rbf(silu_f(v[j + 2])) * v[j + 3]);
+        if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2)
+                if (col0 + j + 1 < p.N) dst[j >> 1] = f2bf(rbf(silu_f(v[j])) * v[j + 1]);
+        }
+    } else {
+        if (EPI == EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = rbf(gelu_erf_f(v[j]));
+        }
+        if (EPI == EPI_RESID) {
+            const bf16* rs = p.resid + (size_t)orow * p.ldr + col0;
+            if (full && (reinterpret_cast<uintptr_t>(rs) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 rv = *reinterpret_cast<const uint4*>(rs + j);
+                    float2 r0 = bf2x_to_f2(rv.x), r1 = bf2x_to_f2(rv.y), r2 = bf2x_to_f2(rv.z), r3 = bf2x_to_f2(rv.w);
+                    v[j] = rbf(r0.x + v[j]); v[j + 1] = rbf(r0.y + v[j + 1]); v[j + 2] = rbf(r1.x + v[j + 2]); v[j + 3] = rbf(r1.y + v[j + 3]);
+                    v[j + 4] = rbf(r2.x + v[j + 4]); v[j + 5] = rbf(r2.y + v[j + 5]); v[j + 6] = rbf(r3.x + v[j + 6]); v[j + 7] = rbf(r3.y + v[j + 7]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col0 + j < p.N) v[j] = rbf(bf2f(rs[j]) + v[j]);
+            }
+        }
+        bf16* dst = p.C + (size_t)orow * p.ldc + col0;
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(dst + j) = make_uint4(f2_to_bf2x(v[j], v[j + 1]), f2_to_bf2x(v[j + 2], v[j + 3]),
+                                                                f2_to_bf2x(v[j + 4], v[j + 5]), f2_to_bf2x(v[j + 6], v[j + 7]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) dst[j] = f2bf(v[j]);
+        }
+    }
+}
+
 template <int BN>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
     static constexpr int B_BYTES = BN * TC_BK * 2;             // 32 / 16 KB
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int TOTAL = TC_STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers, TMEM slot*/;
 };
 
 template <int BN, int EPI>
@@ -148,47 +226,118 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, r);
             const int col0 = n0 + cb;
             if (!row_ok || col0 >= p.N) continue;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float x = __uint_as_float(r[j]);
-                int col = col0 + j;
-                if (p.bias && col < p.N) x += bf2f(p.bias[col]);
-                v[j] = rbf(x);
-            }
-            if (EPI == EPI_SWIGLU) {
-                bf16* dst = p.C + (size_t)orow * p.ldc + (col0 >> 1);
-#pragma unroll
-                for (int j = 0; j < 32; j += 2)
-                    if (col0 + j + 1 < p.N) dst[j >> 1] = f2bf(rbf(silu_f(v[j])) * v[j + 1]);
-            } else {
-                if (EPI == EPI_GELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = rbf(gelu_erf_f(v[j]));
-                }
-                if (EPI == EPI_RESID) {
-                    const bf16* rs = p.resid + (size_t)orow * p.ldr + col0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N) v[j] = rbf(bf2f(rs[j]) + v[j]);
-                }
-                bf16* dst = p.C + (size_t)orow * p.ldc + col0;
-                if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8)
-                        *reinterpret_cast<uint4*>(dst + j) = make_uint4(f2_to_bf2x(v[j], v[j + 1]), f2_to_bf2x(v[j + 2], v[j + 3]),
-                                                                        f2_to_bf2x(v[j + 4], v[j + 5]), f2_to_bf2x(v[j + 6], v[j + 7]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (col0 + j < p.N) dst[j] = f2bf(v[j]);
-                }
-            }
+            epilogue_block<EPI>(p, r, orow, col0);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks tiles (tile = cta, cta + grid, ...).  The TMEM holds TWO accumulators
+// (2 x BN fp32 columns), so the MMA issuer starts tile i+1 while the four epilogue warps drain tile i, and the
+// shared-memory ring runs across tile boundaries (no pipeline drain / refill, no per-tile TMEM allocation, barrier
+// initialisation or tensor-map fetch).  Same arithmetic as the single-tile kernel.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS_P, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, GemmParams p, int tiles_m, int n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TcSmem<BN>::STAGE);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* tmem_full = empty + TC_STAGES;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = (p.K + TC_BK - 1) / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&full[i], 1); tc_mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc_mbar_init(&tmem_full[i], 1); tc_mbar_init(&tmem_empty[i], 8); }   // 8 epilogue warps release an accumulator
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---- TMA producer: k-blocks of all of this CTA's tiles, back to back
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    tc_mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
+                    tc_mbar_expect_tx(&full[s], TcSmem<BN>::STAGE);
+                    uint8_t* sa = smem + s * TcSmem<BN>::STAGE;
+                    tma_load_2d(sa, &map_a, kb * TC_BK, m0, &full[s]);
+                    tma_load_2d(sa + TcSmem<BN>::A_BYTES, &map_w, kb * TC_BK, n0, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---- MMA issuer
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t acc = ti & 1;
+                tc_mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator (first two uses pass)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % TC_STAGES;
+                    tc_mbar_wait(&full[s], (it / TC_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint8_t* sa = smem + s * TcSmem<BN>::STAGE;
+                    const uint64_t adesc = umma_desc_k_sw128(sa), bdesc = umma_desc_k_sw128(sa + TcSmem<BN>::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ---- epilogue warps: TMEM lanes [32*(warp%4), +32); lane = output row inside the tile; warps 2-5 take the first half of
+        //      the accumulator columns, warps 6-9 the second half (the SwiGLU / bias epilogues are otherwise slower than a K = 1280 mainloop)
+        const int q = warp & 3;
+        const int c_lo = warp < 6 ? 0 : BN / 2, c_hi = c_lo + BN / 2;
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
+            const uint32_t acc = ti & 1;
+            tc_mbar_wait(&tmem_full[acc], (ti >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const int orow = row_ok ? (p.out_row_map ? p.out_row_map[row] : row) : 0;
+            for (int cb = c_lo; cb < c_hi; cb += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)cb, r);
+                if (cb + 32 >= c_hi) {
+                    // every accumulator column of this tile is in registers: hand the accumulator back before the last block's math
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+                }
+                const int col0 = n0 + cb;
+                if (!row_ok || col0 >= p.N) continue;
+                epilogue_block<EPI>(p, r, orow, col0);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -220,18 +369,36 @@ int make_map(CUtensorMap* map, const bf16* base, int rows, int cols, int ld, int
     return 0;
 }
 
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
 template <int BN, int EPI>
 int launch_bn(const GemmParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
+        PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
         configured = true;
     }
     CUtensorMap ma, mw;
     RC_RET(make_map(&ma, p.A, p.M, p.K, p.lda, TC_BM));
     RC_RET(make_map(&mw, p.W, p.N, p.K, p.ldw, BN));
-    dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM);
-    gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, st>>>(ma, mw, p);
+    const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + TC_BM - 1) / TC_BM;
+    if (g_padt_gemm_tc == 2) {      // one tile per CTA (first tcgen05 version, kept for A/B measurements)
+        dim3 grid(tiles_n, tiles_m);
+        gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, st>>>(ma, mw, p);
+    } else {
+        const int n_tiles = tiles_n * tiles_m;
+        const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+        gemm_tc_persistent_kernel<BN, EPI><<<grid, TC_THREADS_P, TcSmem<BN>::TOTAL, st>>>(ma, mw, p, tiles_m, n_tiles);
+    }
     PADT_LAUNCH_CHECK();
     return 0;
 }

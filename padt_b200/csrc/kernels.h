@@ -22,7 +22,7 @@ int launch_gemm(int epi, const GemmParams& p, cudaStream_t st);
 // tcgen05 + TMA path for the large shapes (gemm_tc.cu); launch_gemm dispatches to it when eligible and enabled
 bool gemm_tc_eligible(const GemmParams& p);
 int launch_gemm_tc(int epi, const GemmParams& p, cudaStream_t st);
-extern int g_padt_gemm_tc;   // 1 = use the tcgen05 path when eligible (default), 0 = mma.sync only
+extern int g_padt_gemm_tc;   // 1 = persistent tcgen05 kernel when eligible (default), 2 = one-tile tcgen05 kernel, 0 = mma.sync only
 
 // ------------------------------------------------------------------ segmented flash attention (attention.cu)
 struct AttnParams {
