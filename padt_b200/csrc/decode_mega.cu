@@ -31,7 +31,7 @@ constexpr int MK_MAXSLOTS = 24;
 constexpr int MK_GROUP = 8;                   // weight rows per stage (= n of the mma)
 constexpr int MK_MAXGROUPS = 8;               // row groups of one CTA in the small-matrix phases (bias / residual preload)
 constexpr int MK_DEFAULT_PF = 16;               // defaults of PADT_MEGA_PF / PADT_MEGA_FLAGS (see MegaArgs)
-constexpr int MK_DEFAULT_FLAGS = 1 | 4 | 8;      // MF_EVICT_FIRST | MF_KV_SMEM | MF_PF_LINES
+constexpr int MK_DEFAULT_FLAGS = 1 | 4 | 8 | 64; // MF_EVICT_FIRST | MF_KV_SMEM | MF_PF_LINES | MF_STAGE_MIN
 constexpr int MK_DEFAULT_PF_PACE = 0;
 constexpr int MK_ATTN_SMEM = 2 * DA_TILE * DA_LD * 2 + DA_MAXG * DA_HD * 4 + DA_MAXG * DA_TILE * 4;
 
@@ -51,7 +51,7 @@ struct MegaArgs {
     int pf_pace;                  // minimum cycles between two stage prefetches (keeps the request queues short during a stall)
     int attn_off;                 // byte offset of the attention scratch inside the activation region
 };
-enum { MF_EVICT_FIRST = 1, MF_NO_AREG = 2, MF_KV_SMEM = 4, MF_PF_LINES = 8, MF_PF_EVICT_LAST = 16, MF_BAR_FLAGS = 32 };
+enum { MF_EVICT_FIRST = 1, MF_NO_AREG = 2, MF_KV_SMEM = 4, MF_PF_LINES = 8, MF_PF_EVICT_LAST = 16, MF_STAGE_MIN = 64 };
 
 using CSync = NamedSync<1, MK_STHREADS>;
 
@@ -317,12 +317,36 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& targe
 // activation rows -> shared memory, row stride K + 8 elements (the 16-byte pad keeps the A-fragment loads conflict free).
 // ln_w != null: RMSNorm prologue, bit-identical to rmsnorm_kernel / the decode.cu prologue (rms_rstd_warp + rms_apply8).
 __device__ __forceinline__ void stage_x(const bf16* src, const bf16* ln_w, float eps, int K, int B, bf16* xs, int tid, int lane, bf16* copy0,
-                                        bf16* copy1) {
+                                        bf16* copy1, float* s_part, bool min_traffic) {
     if (tid >= MK_CTHREADS) return;
     const int x_ld = K + 8;
     for (int b = 0; b < B; ++b) {
         const bf16* xr = src + (size_t)b * K;
-        if (ln_w) {
+        if (ln_w && min_traffic && K <= 8 * MK_CTHREADS) {
+            // every element of the row is loaded by exactly ONE thread of the CTA (the warp-redundant statistics pass below pulls
+            // 16 x the row through L2 -> L1 in all 148 CTAs at once, right after a barrier has invalidated L1): per-warp partial
+            // sums of squares -> shared memory -> fixed-order total, then the thread normalises the chunk it already holds.
+            const int nch = K >> 3, warp = tid >> 5;
+            const bool mine = tid < nch;
+            uint4 xv = make_uint4(0, 0, 0, 0), wv = xv;
+            if (mine) { xv = *reinterpret_cast<const uint4*>(xr + tid * 8); wv = *reinterpret_cast<const uint4*>(ln_w + tid * 8); }
+            float2 e0 = bf2x_to_f2(xv.x), e1 = bf2x_to_f2(xv.y), e2 = bf2x_to_f2(xv.z), e3 = bf2x_to_f2(xv.w);
+            float ss = e0.x * e0.x + e0.y * e0.y + e1.x * e1.x + e1.y * e1.y + e2.x * e2.x + e2.y * e2.y + e3.x * e3.x + e3.y * e3.y;
+            ss = warp_sum(ss);
+            if (lane == 0) s_part[warp] = ss;
+            asm volatile("bar.sync 2, %0;" ::"n"(MK_CTHREADS) : "memory");
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < MK_CW; ++w) tot += s_part[w];
+            const float rstd = 1.0f / sqrtf(tot / (float)K + eps);
+            if (mine) {
+                uint4 o = rms_apply8(xv, wv, rstd);
+                *reinterpret_cast<uint4*>(xs + (size_t)b * x_ld + tid * 8) = o;
+                if (copy0) *reinterpret_cast<uint4*>(copy0 + (size_t)b * K + tid * 8) = o;
+                if (copy1) *reinterpret_cast<uint4*>(copy1 + (size_t)b * K + tid * 8) = o;
+            }
+            if (b + 1 < B) asm volatile("bar.sync 2, %0;" ::"n"(MK_CTHREADS) : "memory");   // s_part is reused by the next row
+        } else if (ln_w) {
             // the norm weights do not depend on the statistics: fetch this thread's first chunk before the reduction, so the
             // apply pass does not start with a second dependent L2 round trip
             uint4 w0 = make_uint4(0, 0, 0, 0);
@@ -559,6 +583,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     __shared__ volatile unsigned int s_prog;
     __shared__ long long s_prod_wait;
     __shared__ DecodeLayerW s_w[2];
+    __shared__ float s_part[MK_CW];
     __shared__ ArgMax am;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -704,7 +729,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         const int tk = k < 5 ? k : 5;
         TSTART();
         if (stage) {
-            stage_x(src, ln, p.eps, K, p.B, xs, tid, lane, copy0, copy1);
+            stage_x(src, ln, p.eps, K, p.B, xs, tid, lane, copy0, copy1, s_part, (a.flags & MF_STAGE_MIN) != 0);
             CSync()();
         }
         TADD(t_stage[tk]); TSTART();
