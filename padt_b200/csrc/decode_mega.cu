@@ -66,7 +66,47 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+// -DPADT_MK_WATCHDOG: every wait site reports itself and traps after ~2 s instead of hanging the GPU (debug builds only)
+#ifdef PADT_MK_WATCHDOG
+__device__ int g_wd_phase[160];
+__device__ int g_wd_sub[160];     // finer position inside the phase (written by tid 0)
+__device__ int g_wd_epi[160];     // groups finished by the epilogue warp
+__device__ int g_wd_prod[160];    // last stage issued by producer lane 0
+#define WD_MARK(arr, v) do { ((volatile int*)arr)[blockIdx.x] = (v); } while (0)
+#define WD_DECL(site) long long _wd_t0 = clock64(); const int _wd_site = (site)
+#define WD_CHECK()                                                                                                              \
+    do {                                                                                                                        \
+        if (clock64() - _wd_t0 > 4000000000LL) {                                                                                \
+            printf("[watchdog] site %d cta %d warp %d lane %d phase %d\n", _wd_site, blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31, \
+                   g_wd_phase[blockIdx.x]);                                                                                     \
+            if (blockIdx.x == 0 || blockIdx.x == 1) {                                                                           \
+                for (int _c = 0; _c < (int)gridDim.x; ++_c) printf("[watchdog] cta %d phase %d sub %d epi_groups %d producer_stage %d\n", _c, ((volatile int*)g_wd_phase)[_c], ((volatile int*)g_wd_sub)[_c], ((volatile int*)g_wd_epi)[_c], ((volatile int*)g_wd_prod)[_c]); \
+                long long _t1 = clock64();                                                                                      \
+                while (clock64() - _t1 < 200000000LL) {}                                                                        \
+            } else {                                                                                                            \
+                long long _t1 = clock64();                                                                                      \
+                while (clock64() - _t1 < 400000000LL) {}                                                                        \
+            }                                                                                                                   \
+            __trap();                                                                                                           \
+        }                                                                                                                       \
+    } while (0)
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int site) {
+    WD_DECL(site);
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        WD_CHECK();
+    }
+}
+#else
+#define WD_MARK(arr, v) do { } while (0)
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int site = 0) {
+#if defined(PADT_MK_WATCHDOG) && PADT_MK_WATCHDOG >= 2
+    mbar_wait_wd(smem_u32(b), parity, site);
+    return;
+#endif
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -189,12 +229,12 @@ __device__ void producer_loop(const MegaArgs& a, uint8_t* ring, uint64_t* full, 
         for (int i = lane; i < n; i += ns, parity ^= 1) {
             StageDesc d = tab[i];
             long long tq = (a.dbg & 1) ? clock64() : 0;
-            mbar_wait(&empty[lane], parity ^ 1);
+            mbar_wait(&empty[lane], parity ^ 1, 1);
             if (a.dbg & 1) tw += clock64() - tq;
             mbar_expect_tx(&full[lane], d.bytes);
             if (hint) tma_bulk_g2s_hint(dst, d.src, d.bytes, &full[lane], pol);
             else tma_bulk_g2s(dst, d.src, d.bytes, &full[lane]);
-            if (lane == 0) *prog = (unsigned int)i;     // issue frontier, read by the L2 prefetch warp
+            if (lane == 0) { *prog = (unsigned int)i; WD_MARK(g_wd_prod, i); }     // issue frontier, read by the L2 prefetch warp
         }
         if (lane == 0) { *prog = (unsigned int)n; *t_wait_empty = tw; }
     }
@@ -214,7 +254,7 @@ __device__ void producer_loop(const MegaArgs& a, uint8_t* ring, uint64_t* full, 
         for (int sg = 0; sg < s.nseg; ++sg, ++it) {
             int slot = it % ns;
             uint32_t par = (it / ns) & 1;
-            mbar_wait(&empty[slot], par ^ 1);
+            mbar_wait(&empty[slot], par ^ 1, 2);
             mbar_expect_tx(&full[slot], seg_bytes * rows);
             uint8_t* dst = ring + (size_t)slot * a.slot_bytes;
             const bf16* src = s.base + (size_t)(g * MK_GROUP) * s.K + (size_t)sg * s.Kseg;
@@ -271,7 +311,11 @@ __device__ void prefetch_loop(const MegaArgs& a, int cta, int lane, volatile uns
 // Shared-memory operations on 32-bit shared-window addresses: the addresses are computed once per phase, so the inner loops
 // carry no generic->shared conversions or index arithmetic (the v3 loop spent ~35 instructions per two k-steps on them and was
 // ISSUE bound at ~700 cycles per 16 KB stage, i.e. no faster than HBM delivers a stage).
-__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity, int site = 0) {
+#if defined(PADT_MK_WATCHDOG) && PADT_MK_WATCHDOG >= 2
+    mbar_wait_wd(bar, parity, site);
+    return;
+#endif
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -309,7 +353,12 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& targe
     target += (unsigned int)G;
     if (tid == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+#ifdef PADT_MK_WATCHDOG
+        WD_DECL(6);
+        while (ld_acquire_u32(bar) < target) WD_CHECK();
+#else
         while (ld_acquire_u32(bar) < target) {}
+#endif
     }
     CSync()();
 }
@@ -410,7 +459,7 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
         }
         for (int gi = 0; gi < s.groups; ++gi, ++g_idx) {
             const uint32_t buf = g_idx % MK_NRED;
-            mbar_wait_s(sm.red_full + buf * 8, (g_idx / MK_NRED) & 1);
+            mbar_wait_s(sm.red_full + buf * 8, (g_idx / MK_NRED) & 1, 3);
             const float* red = sm.red + (size_t)buf * MK_CW * B * 8;
             const int r = gi * 8 + en;
             if (r < s.rows && !(a.dbg & 2)) {
@@ -443,7 +492,7 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_s(sm.red_empty + buf * 8);
+            if (lane == 0) { mbar_arrive_s(sm.red_empty + buf * 8); WD_MARK(g_wd_epi, (int)g_idx); }
         }
         return;
     }
@@ -475,7 +524,7 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
             const uint32_t my_slot = slot, my_parity = parity;
             if (++slot == (uint32_t)n_slots) { slot = 0; parity ^= 1u; }
             if (s.nseg > 1 ? ((sg & 1) != set) : (set != 0)) continue;          // the other half owns this stage
-            mbar_wait_s(sm.full + my_slot * 8, my_parity);
+            mbar_wait_s(sm.full + my_slot * 8, my_parity, 4);
             if (!skip_math) {
                 const uint32_t wb = sm.ring + my_slot * (uint32_t)a.slot_bytes + w_off;
                 if (reg_path) {
@@ -512,7 +561,7 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
         const float r0 = c[0] + c2[0], r1 = c[1] + c2[1];
         // hand the K-slice partial of this row group to the epilogue warp
         const uint32_t buf = g_idx % MK_NRED;
-        mbar_wait_s(sm.red_empty + buf * 8, ((g_idx / MK_NRED) & 1) ^ 1);
+        mbar_wait_s(sm.red_empty + buf * 8, ((g_idx / MK_NRED) & 1) ^ 1, 5);
         if (live) {
             float* red = sm.red + ((size_t)(buf * MK_CW + warp) * B + g) * 8;
             red[2 * t] = r0;
@@ -665,6 +714,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     static_assert(sizeof(DecodeLayerW) % 4 == 0 && sizeof(DecodeLayerW) / 4 <= 32, "layer descriptor is copied by one warp");
     for (int ph = 0; ph < n_phase; ++ph) {
         const int li = ph / 5, k = ph < p.n_layers * 5 ? ph % 5 : 5 + (ph - p.n_layers * 5);   // k: 0..4 layer phases, 5 head, 6 prototypes
+#ifdef PADT_MK_WATCHDOG
+        if (tid == 0) { WD_MARK(g_wd_phase, ph); WD_MARK(g_wd_sub, 0); }
+#endif
         if (k == 3 && li + 1 < p.n_layers && warp == 0 && lane < (int)(sizeof(DecodeLayerW) / 4))
             // next layer's descriptor -> shared memory during the long gate/up phase (a global load at the layer start would sit
             // on the critical path right after a barrier has invalidated L1)
@@ -683,17 +735,26 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
             // ---- M-RoPE + KV append + split-KV attention; the n_split CTAs of a (row, kv head) then combine slices of the result
             TSTART();
             if (has_item) {
+                if (tid == 0) WD_MARK(g_wd_sub, 3);
                 decode_attn_body<false>(attn_args(li), a_split, a_kvh, a_b, attn_smem, tid, MK_STHREADS, CSync(), kv_in_flight);
                 __threadfence();
                 CSync()();
+                if (tid == 0) WD_MARK(g_wd_sub, 4);
                 if (tid == 0) {
                     unsigned int* cnt = reinterpret_cast<unsigned int*>(p.attn_counters) + p.B * p.nkv + a_b * p.nkv + a_kvh;   // monotonic counters
                     const unsigned int want = (step_idx * (unsigned int)p.n_layers + (unsigned int)li + 1u) * (unsigned int)p.n_split;
                     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+#ifdef PADT_MK_WATCHDOG
+                    WD_DECL(7);
+                    while (ld_acquire_u32(cnt) < want) WD_CHECK();
+#else
                     while (ld_acquire_u32(cnt) < want) {}
+#endif
                 }
                 CSync()();
+                if (tid == 0) WD_MARK(g_wd_sub, 5);
                 attn_merge_slice(p, a_b, a_kvh, a_split, tid);
+                if (tid == 0) WD_MARK(g_wd_sub, 6);
             }
             TADD(t_work[1]); TSTART();
             grid_sync(a.gbar, target, G, tid, a.dbg);
@@ -733,7 +794,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
             CSync()();
         }
         TADD(t_stage[tk]); TSTART();
+        if (tid == 0) WD_MARK(g_wd_sub, 1);
         consume_seg(a, s, ep, sm, it, grp, tid, bias, y, n_out, am);
+        if (tid == 0) WD_MARK(g_wd_sub, 2);
         TADD(t_work[tk]); TSTART();
         if (k < 5) grid_sync(a.gbar, target, G, tid, a.dbg);
         TADD(t_bar[tk]);
@@ -823,7 +886,13 @@ int decode_mega_plan(const DecodeParams& p, int* slot_bytes, int* n_slots, int* 
     int fixed = xb + (2 * MK_MAXSLOTS + 2 * MK_NRED) * 8 + MK_NRED * MK_CW * p.B * 8 * 4;
     int ns = (budget - fixed) / sb;
     ns = ns > MK_MAXSLOTS ? MK_MAXSLOTS : ns;
-    if (ns < 3) return -1;
+    // EVEN slot count: the two half-CTAs take alternate stages, and a half only waits on the `full` barriers of its own stages.
+    // With an even ring every slot always belongs to the same half, so a waiter is never more than one phase behind its barrier.
+    // With an odd ring a half skips every other use of a slot, and when it runs ahead of the other half (up to MK_NRED row groups,
+    // i.e. more than a ring revolution when a group has 16 stages) the parity test passes on the OTHER half's data
+    // (seen at I = 18944: 9 slots -> wrong data, double arrivals, launch failure / hang).
+    ns &= ~1;
+    if (ns < 4) return -1;
     *slot_bytes = sb; *n_slots = ns; *x_bytes = xb;
     *smem_bytes = (size_t)ns * sb + fixed;
     return 0;
