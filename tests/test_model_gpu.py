@@ -222,3 +222,44 @@ def test_persistent_decode_kernel_matches_per_layer_kernels(name):
     for impl_out in (a, b):
         eq, flips = check_tokens_margin(impl_out.argmax_tokens.t(), fx["forced_argmax"], fx["forced_top2"], name)
         assert eq >= 0.8 * (eq + flips)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("dims", [dict(D=3584, I=18944, nh=28, nkv=4), dict(D=2048, I=18944, nh=16, nkv=2), dict(D=3584, I=11008, nh=28, nkv=4)],
+                         ids=["7B_dims", "3B_I18944", "7B_I11008"])
+def test_persistent_decode_kernel_at_7b_projection_shapes(dims):
+    """PaDT_Pro_7B projection shapes (2 layers, small vocabulary so the weights stay below 2 GB): K = 18944 needs 16 ring stages per
+    row group and 19 KB stages, K = 3584 four stages -- different stage / slot geometry than 3B.  Regression test for the odd
+    ring-slot-count bug (a half-CTA passed the full-barrier parity test on the other half's stage: launch failure / hang at
+    I = 18944).  The persistent kernel must agree with the per-layer kernels and with CUDA-graph replay of itself."""
+    from padt_b200.config import PadtConfig, VisionConfig, TextConfig, DecoderConfig
+    from padt_b200.modeling import PaDTForConditionalGeneration
+    vocab = 4096
+    cfg = PadtConfig(name="7b_shapes", vision=VisionConfig(depth=2, fullatt_block_indexes=(1,), out_hidden_size=dims["D"]),
+                     text=TextConfig(hidden_size=dims["D"], intermediate_size=dims["I"], num_layers=2, num_heads=dims["nh"], num_kv_heads=dims["nkv"],
+                                     vocab_size=vocab, tie_word_embeddings=False),
+                     decoder=DecoderConfig(), image_token_id=vocab - 12, video_token_id=vocab - 11, vision_start_token_id=vocab - 14,
+                     vision_end_token_id=vocab - 13, eos_token_ids=(vocab - 10,), pad_token_id=vocab - 9)
+    model = PaDTForConditionalGeneration.from_random(cfg, seed=3, device="cuda:0")
+    side = 24
+    P = side * side
+    g = torch.Generator().manual_seed(5)
+    pv = torch.randn((P, cfg.vision.patch_dim), generator=g).to(torch.bfloat16).cuda()
+    M = P // 4
+    row = torch.randint(0, vocab - 20, (14,), generator=g).tolist() + [cfg.vision_start_token_id] + [cfg.image_token_id] * M + \
+        [cfg.vision_end_token_id] + torch.randint(0, vocab - 20, (30,), generator=g).tolist()
+    ids = torch.tensor([row]).cuda()
+    steps = 6
+    forced = torch.randint(0, vocab - 20, (1, steps), generator=g).cuda()     # teacher forcing keeps the three runs on the same inputs
+    kw = dict(input_ids=ids, attention_mask=torch.ones_like(ids), pixel_values=pv, image_grid_thw=torch.tensor([[1, side, side]]).cuda(),
+              max_new_tokens=steps, return_dict_in_generate=True, eos_token_id=[], output_hidden_states=True, forced_tokens=forced)
+    outs = {}
+    for impl, graph in ((0, 0), (1, 0), (1, 1)):
+        model.engine.set_option("decode_impl", impl)
+        model.engine.set_option("use_graph", graph)
+        outs[(impl, graph)] = model.generate(**kw)
+    torch.cuda.synchronize()
+    a, b, c = outs[(0, 0)], outs[(1, 0)], outs[(1, 1)]
+    assert torch.equal(b.argmax_tokens, c.argmax_tokens) and torch.equal(b.hidden_states[-1][-1], c.hidden_states[-1][-1])
+    for s in range(1, steps):
+        assert_close_bf16(b.hidden_states[s][-1], a.hidden_states[s][-1], f"hidden step {s}", rel_to_max=0.02, cos=0.9995)
