@@ -31,7 +31,7 @@ constexpr int MK_MAXSLOTS = 24;
 constexpr int MK_GROUP = 8;                   // weight rows per stage (= n of the mma)
 constexpr int MK_MAXGROUPS = 8;               // row groups of one CTA in the small-matrix phases (bias / residual preload)
 constexpr int MK_DEFAULT_PF = 16;               // defaults of PADT_MEGA_PF / PADT_MEGA_FLAGS (see MegaArgs)
-constexpr int MK_DEFAULT_FLAGS = 1 | 4 | 8 | 64; // MF_EVICT_FIRST | MF_KV_SMEM | MF_PF_LINES | MF_STAGE_MIN
+constexpr int MK_DEFAULT_FLAGS = 1 | 4 | 8 | 64 | 128; // MF_EVICT_FIRST | MF_KV_SMEM | MF_PF_LINES | MF_STAGE_MIN | MF_SPLIT
 constexpr int MK_DEFAULT_PF_PACE = 0;
 constexpr int MK_ATTN_SMEM = 2 * DA_TILE * DA_LD * 2 + DA_MAXG * DA_HD * 4 + DA_MAXG * DA_TILE * 4;
 
@@ -51,7 +51,7 @@ struct MegaArgs {
     int pf_pace;                  // minimum cycles between two stage prefetches (keeps the request queues short during a stall)
     int attn_off;                 // byte offset of the attention scratch inside the activation region
 };
-enum { MF_EVICT_FIRST = 1, MF_NO_AREG = 2, MF_KV_SMEM = 4, MF_PF_LINES = 8, MF_PF_EVICT_LAST = 16, MF_STAGE_MIN = 64 };
+enum { MF_EVICT_FIRST = 1, MF_NO_AREG = 2, MF_KV_SMEM = 4, MF_PF_LINES = 8, MF_PF_EVICT_LAST = 16, MF_STAGE_MIN = 64, MF_SPLIT = 128 };
 
 using CSync = NamedSync<1, MK_STHREADS>;
 
@@ -146,10 +146,14 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t& r0, uint32_t& r1, const vo
 struct Seg {
     const bf16* img;    // stage image of this CTA's first row group (nullptr: row-major source, one copy per row)
     const bf16* base;   // row `row_lo` of the row-major matrix (used when img == nullptr)
-    int row_lo;         // first global output row of this CTA's slice
+    int row_lo;         // first global output row of this CTA's slice (group-aligned partition)
     int rows;           // valid rows in the slice (the last group may be ragged)
     int groups;         // ceil(rows / 8)
     int K, Kseg, nseg;  // row length, columns per stage, stages per row group
+    // stage-granular view: this CTA consumes stages [st_lo, st_hi) of the matrix, stage = group * nseg + K segment.  With the
+    // balanced partition (MF_SPLIT) the range may begin / end inside a row group; that group is then shared with a neighbour CTA.
+    int st_lo, st_hi;
+    int row_begin, n_rows;   // first output row of the matrix, rows of the matrix
 };
 
 // columns per stage: K / nseg (multiple of 16) with the smallest nseg whose 8-row stage fits one ring slot
@@ -163,9 +167,9 @@ __host__ __device__ inline int pick_nseg(int K, int slot_bytes) {
 }
 
 __device__ __forceinline__ Seg make_seg(const bf16* W, const bf16* img, int nseg_packed, int row_begin, int n_rows, int K, int cta, int G,
-                                         int slot_bytes) {
+                                         int slot_bytes, bool split = false) {
     Seg s;
-    const unsigned int groups = (unsigned int)(n_rows + MK_GROUP - 1) / MK_GROUP;       // groups * G < 2^31 for every matrix here
+    const unsigned int groups = (unsigned int)(n_rows + MK_GROUP - 1) / MK_GROUP;       // groups * nseg * G < 2^31 for every matrix here
     const int lo = (int)((groups * (unsigned int)cta) / (unsigned int)G), hi = (int)((groups * (unsigned int)(cta + 1)) / (unsigned int)G);
     int r_lo = lo * MK_GROUP, r_hi = hi * MK_GROUP;
     r_hi = r_hi > n_rows ? n_rows : r_hi;
@@ -177,6 +181,14 @@ __device__ __forceinline__ Seg make_seg(const bf16* W, const bf16* img, int nseg
     s.nseg = img ? nseg_packed : pick_nseg(K, slot_bytes);
     s.Kseg = K / s.nseg;
     s.img = img ? img + (size_t)lo * s.nseg * MK_GROUP * (s.Kseg + 8) : nullptr;
+    s.row_begin = row_begin; s.n_rows = n_rows;
+    if (split && img && groups >= (unsigned int)G) {     // every CTA gets >= nseg stages, so a row group spans at most two CTAs
+        const unsigned int S = groups * (unsigned int)s.nseg;
+        s.st_lo = (int)((S * (unsigned int)cta) / (unsigned int)G);
+        s.st_hi = (int)((S * (unsigned int)(cta + 1)) / (unsigned int)G);
+    } else {
+        s.st_lo = lo * s.nseg; s.st_hi = hi * s.nseg;
+    }
     return s;
 }
 
@@ -184,11 +196,15 @@ enum { SEG_QKV = 0, SEG_O = 1, SEG_GU = 2, SEG_DOWN = 3 };
 
 __device__ __forceinline__ Seg layer_seg(const MegaArgs& a, const DecodeLayerW& w, int which, int cta, int G) {
     const DecodeParams& p = a.p;
+    // Balanced (stage-granular) partition only for down_proj: it is the HBM-bound phase with the coarsest quantisation (256 row groups
+    // of 8 stages for 148 CTAs).  Measured on q/k/v, o_proj and gate/up (2 stages per group, one per half-CTA) it LOSES: a shared
+    // group with a single stage keeps one half-CTA idle, so the phase gets longer by one stage time.
+    const bool split = (a.flags & MF_SPLIT) != 0;
     switch (which) {
-        case SEG_QKV: return make_seg(w.wqkv, w.iqkv, p.nseg_d, 0, (p.nh + 2 * p.nkv) * p.hd, p.D, cta, G, a.slot_bytes);
-        case SEG_O: return make_seg(w.wo, w.io, p.nseg_a, 0, p.D, p.nh * p.hd, cta, G, a.slot_bytes);
-        case SEG_GU: return make_seg(w.wgu, w.igu, p.nseg_d, 0, 2 * p.I, p.D, cta, G, a.slot_bytes);
-        default: return make_seg(w.wdown, w.idown, p.nseg_i, 0, p.D, p.I, cta, G, a.slot_bytes);
+        case SEG_QKV: return make_seg(w.wqkv, w.iqkv, p.nseg_d, 0, (p.nh + 2 * p.nkv) * p.hd, p.D, cta, G, a.slot_bytes, false);
+        case SEG_O: return make_seg(w.wo, w.io, p.nseg_a, 0, p.D, p.nh * p.hd, cta, G, a.slot_bytes, false);
+        case SEG_GU: return make_seg(w.wgu, w.igu, p.nseg_d, 0, 2 * p.I, p.D, cta, G, a.slot_bytes, false);
+        default: return make_seg(w.wdown, w.idown, p.nseg_i, 0, p.D, p.I, cta, G, a.slot_bytes, split);
     }
 }
 
@@ -433,37 +449,66 @@ struct ArgMax { float v[2][32]; int i[2][32]; int lo[2][32], hi[2][32]; };   // 
 // never waits for the other warps.  Epilogue warp (16): waits for the 16 partials of a group, adds them in warp order and
 // applies the HF epilogue.
 __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int ep, const SmemMap& sm, uint32_t& it, uint32_t& grp, int tid,
-                                            const bf16* bias, bf16* y, int n_out, ArgMax& am) {
+                                            const bf16* bias, bf16* y, int n_out, ArgMax& am, unsigned int epoch) {
     const DecodeParams& p = a.p;
     const int warp = tid >> 5, lane = tid & 31;
     const int B = p.B;
     const int n_slots = a.n_slots;
     uint32_t slot = it % (uint32_t)n_slots, parity = (it / (uint32_t)n_slots) & 1u;
-    it += (uint32_t)s.groups * s.nseg;
+    const int n_st = s.st_hi - s.st_lo;
+    const int g_first = s.st_lo / s.nseg;                                   // first (possibly shared) row group of this CTA
+    const int n_grp = n_st > 0 ? (s.st_hi - 1) / s.nseg - g_first + 1 : 0;  // row groups touched (whole or partial)
+    it += (uint32_t)n_st;
     uint32_t g_idx = grp;
-    grp += (uint32_t)s.groups;
+    grp += (uint32_t)n_grp;
     if (warp == MK_CW) {
         // ================= epilogue warp: lane -> (batch row eb = pass*4 + lane/8, weight row en = lane%8)
+        // A row group whose K segments are shared with a neighbour CTA (balanced partition): the CTA holding the TAIL segments
+        // publishes its fp32 partial sums (it meets that group first), the CTA holding the HEAD segments adds them to its own
+        // (it meets the group last, the partial has long been published) and applies the epilogue.  Fixed order: head + tail.
         const int en = lane & 7;
+        const bool tail_first = n_grp > 0 && (s.st_lo % s.nseg) != 0;      // group 0 of this CTA: its head lives in CTA - 1
+        const bool head_last = n_grp > 0 && (s.st_hi % s.nseg) != 0;       // last group: its tail lives in CTA + 1
         if (ep == EP_BIAS || ep == EP_RESID) {   // preload so that the per-group epilogue never waits on global memory
             for (int pass = 0; pass * 4 < B; ++pass) {
                 int eb = pass * 4 + (lane >> 3);
                 if (eb < B)
-                    for (int gi = 0; gi < s.groups && gi < MK_MAXGROUPS; ++gi) {
-                        int r = gi * 8 + en;
-                        if (r < s.rows)
-                            sm.pre[eb * (MK_MAXGROUPS * 8) + r] = ep == EP_BIAS ? (bias ? bf2f(bias[s.row_lo + r]) : 0.f) : bf2f(y[(size_t)eb * n_out + s.row_lo + r]);
+                    for (int gi = tail_first ? 1 : 0; gi < n_grp && gi < MK_MAXGROUPS; ++gi) {
+                        int r = (g_first + gi) * 8 + en;
+                        if (r < s.n_rows)
+                            sm.pre[eb * (MK_MAXGROUPS * 8) + gi * 8 + en] =
+                                ep == EP_BIAS ? (bias ? bf2f(bias[s.row_begin + r]) : 0.f) : bf2f(y[(size_t)eb * n_out + s.row_begin + r]);
                     }
             }
             __syncwarp();
         }
-        for (int gi = 0; gi < s.groups; ++gi, ++g_idx) {
+        for (int gi = 0; gi < n_grp; ++gi, ++g_idx) {
             const uint32_t buf = g_idx % MK_NRED;
+            const bool is_tail = gi == 0 && tail_first, is_head = gi == n_grp - 1 && head_last;
+            float nb0[2] = {0.f, 0.f}, nb1[2] = {0.f, 0.f};                 // neighbour's partial: rows en / en + 1, batch rows of pass 0 / 1
+            if (is_head) {
+                // fetched while the consumer warps are still multiplying this group.  Each partial travels as ONE 64-bit word
+                // {epoch, fp32 bits}: no flag, no fence on the writer, one L2 round trip on the reader.
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int eb = pass * 4 + (lane >> 3);
+                    if (eb < B) {
+                        const unsigned long long* xp = p.xpart + ((size_t)(blockIdx.x + 1) * 8 + eb) * 8;
+                        unsigned long long w0, w1;
+                        do {
+                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w0) : "l"(xp + en) : "memory");
+                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w1) : "l"(xp + (en | 1)) : "memory");
+                        } while ((unsigned int)(w0 >> 32) != epoch || (unsigned int)(w1 >> 32) != epoch);
+                        nb0[pass] = __uint_as_float((unsigned int)w0);
+                        nb1[pass] = __uint_as_float((unsigned int)w1);
+                    }
+                }
+            }
             mbar_wait_s(sm.red_full + buf * 8, (g_idx / MK_NRED) & 1, 3);
             const float* red = sm.red + (size_t)buf * MK_CW * B * 8;
-            const int r = gi * 8 + en;
-            if (r < s.rows && !(a.dbg & 2)) {
-                const int n = s.row_lo + r;
+            const int r = (g_first + gi) * 8 + en;
+            if (!(a.dbg & 2)) {
+                const int n = s.row_begin + r;
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {              // static indices keep the arg-max state in registers
                     const int eb = pass * 4 + (lane >> 3);
@@ -471,13 +516,20 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
                     float sum = 0.f;
 #pragma unroll
                     for (int w = 0; w < MK_CW; ++w) sum += red[(w * B + eb) * 8 + en];
+                    if (is_tail) {                                  // publish: the neighbour finishes this group
+                        const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(sum);
+                        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.xpart + ((size_t)blockIdx.x * 8 + eb) * 8 + en), "l"(w) : "memory");
+                        continue;
+                    }
+                    if (r >= s.n_rows) continue;
+                    sum += nb0[pass];
                     if (ep == EP_BIAS) {
-                        y[(size_t)eb * n_out + n] = f2bf(sum + sm.pre[eb * (MK_MAXGROUPS * 8) + r]);
+                        y[(size_t)eb * n_out + n] = f2bf(sum + sm.pre[eb * (MK_MAXGROUPS * 8) + gi * 8 + en]);
                     } else if (ep == EP_RESID) {
-                        y[(size_t)eb * n_out + n] = f2bf(sm.pre[eb * (MK_MAXGROUPS * 8) + r] + rbf(sum));
+                        y[(size_t)eb * n_out + n] = f2bf(sm.pre[eb * (MK_MAXGROUPS * 8) + gi * 8 + en] + rbf(sum));
                     } else if (ep == EP_SWIGLU) {
                         if ((en & 1) == 0) {   // even row = gate_j, odd row = up_j of the interleaved weight
-                            float up = 0.f;
+                            float up = nb1[pass];
 #pragma unroll
                             for (int w = 0; w < MK_CW; ++w) up += red[(w * B + eb) * 8 + en + 1];
                             float gv = rbf(sum), uv = rbf(up);
@@ -492,7 +544,10 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
                 }
             }
             __syncwarp();
-            if (lane == 0) { mbar_arrive_s(sm.red_empty + buf * 8); WD_MARK(g_wd_epi, (int)g_idx); }
+            if (lane == 0) {
+                mbar_arrive_s(sm.red_empty + buf * 8);
+                WD_MARK(g_wd_epi, (int)g_idx);
+            }
         }
         return;
     }
@@ -518,9 +573,10 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
         }
     }
     const bool skip_math = (a.dbg & (2 | 64)) != 0;
-    for (int gi = 0; gi < s.groups; ++gi, ++g_idx) {
+    int sg = s.st_lo % s.nseg;                                              // the first group may start in the middle (balanced partition)
+    for (int idx = s.st_lo; idx < s.st_hi; ++g_idx) {
         float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int sg = 0; sg < s.nseg; ++sg) {
+        for (; sg < s.nseg && idx < s.st_hi; ++sg, ++idx) {
             const uint32_t my_slot = slot, my_parity = parity;
             if (++slot == (uint32_t)n_slots) { slot = 0; parity ^= 1u; }
             if (s.nseg > 1 ? ((sg & 1) != set) : (set != 0)) continue;          // the other half owns this stage
@@ -558,6 +614,7 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
             __syncwarp();
             if (lane == 0) mbar_arrive_s(sm.empty + my_slot * 8);
         }
+        sg = 0;
         const float r0 = c[0] + c2[0], r1 = c[1] + c2[1];
         // hand the K-slice partial of this row group to the epilogue warp
         const uint32_t buf = g_idx % MK_NRED;
@@ -795,7 +852,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         }
         TADD(t_stage[tk]); TSTART();
         if (tid == 0) WD_MARK(g_wd_sub, 1);
-        consume_seg(a, s, ep, sm, it, grp, tid, bias, y, n_out, am);
+        consume_seg(a, s, ep, sm, it, grp, tid, bias, y, n_out, am, step_idx * (unsigned int)n_phase + (unsigned int)ph + 1u);
         if (tid == 0) WD_MARK(g_wd_sub, 2);
         TADD(t_work[tk]); TSTART();
         if (k < 5) grid_sync(a.gbar, target, G, tid, a.dbg);
@@ -899,41 +956,44 @@ int decode_mega_plan(const DecodeParams& p, int* slot_bytes, int* n_slots, int* 
 }
 
 // Host mirror of make_seg/layer_seg: flattens the image-backed stages of every CTA (same order as the consumers walk them).
-int decode_mega_build_table(const DecodeParams& p, const DecodeLayerW* layers_host, int G, std::vector<uint64_t>& tab, std::vector<int>& off) {
+int decode_mega_build_table(const DecodeParams& p, const DecodeLayerW* layers_host, int G, bool split, std::vector<uint64_t>& tab, std::vector<int>& off) {
     tab.clear();
     off.assign(G + 1, 0);
-    auto add_seg = [&](const bf16* img, int n_rows, int K) {
-        // appended per CTA below
-        (void)img; (void)n_rows; (void)K;
-    };
-    (void)add_seg;
     for (int c = 0; c < G; ++c) {
         off[c] = (int)(tab.size() / 2);
-        auto emit = [&](const bf16* img, int n_rows, int K) {
-            int nseg = decode_mega_nseg(K);
-            int Kseg = K / nseg;
-            int groups = (n_rows + MK_GROUP - 1) / MK_GROUP;
-            long long lo = ((long long)groups * c) / G, hi = ((long long)groups * (c + 1)) / G;
-            uint32_t bytes = MK_GROUP * ((uint32_t)Kseg * 2 + 16);
-            for (long long g = lo; g < hi; ++g)
-                for (int sg = 0; sg < nseg; ++sg) {
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(img) + (size_t)(g * nseg + sg) * bytes;
-                    tab.push_back((uint64_t)(uintptr_t)src);
-                    tab.push_back((uint64_t)bytes);
-                }
+        auto emit = [&](const bf16* img, int n_rows, int K, bool balanced) {
+            const int nseg = decode_mega_nseg(K);
+            const int Kseg = K / nseg;
+            const unsigned int groups = (unsigned int)(n_rows + MK_GROUP - 1) / MK_GROUP;
+            unsigned int lo, hi;                       // stage range, same arithmetic as make_seg
+            if (balanced && groups >= (unsigned int)G) {
+                const unsigned int S = groups * (unsigned int)nseg;
+                lo = (S * (unsigned int)c) / (unsigned int)G; hi = (S * (unsigned int)(c + 1)) / (unsigned int)G;
+            } else {
+                lo = ((groups * (unsigned int)c) / (unsigned int)G) * nseg; hi = ((groups * (unsigned int)(c + 1)) / (unsigned int)G) * nseg;
+            }
+            const uint32_t bytes = MK_GROUP * ((uint32_t)Kseg * 2 + 16);
+            for (unsigned int st = lo; st < hi; ++st) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(img) + (size_t)st * bytes;
+                tab.push_back((uint64_t)(uintptr_t)src);
+                tab.push_back((uint64_t)bytes);
+            }
         };
         for (int li = 0; li < p.n_layers; ++li) {
             const DecodeLayerW& w = layers_host[li];
-            emit(w.iqkv, (p.nh + 2 * p.nkv) * p.hd, p.D);
-            emit(w.io, p.D, p.nh * p.hd);
-            emit(w.igu, 2 * p.I, p.D);
-            emit(w.idown, p.D, p.I);
+            emit(w.iqkv, (p.nh + 2 * p.nkv) * p.hd, p.D, false);
+            emit(w.io, p.D, p.nh * p.hd, false);
+            emit(w.igu, 2 * p.I, p.D, false);
+            emit(w.idown, p.D, p.I, split);        // see layer_seg
         }
-        emit(p.head_img, p.vocab, p.D);
+        emit(p.head_img, p.vocab, p.D, false);
     }
     off[G] = (int)(tab.size() / 2);
     return 0;
 }
+
+int decode_mega_flags() { return getenv("PADT_MEGA_FLAGS") ? atoi(getenv("PADT_MEGA_FLAGS")) : MK_DEFAULT_FLAGS; }
+bool decode_mega_split() { return (decode_mega_flags() & MF_SPLIT) != 0; }
 
 int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, const void* stage_tab, const int* stage_off, unsigned int* gbar,
                        int n_sms, cudaStream_t st) {
@@ -945,7 +1005,7 @@ int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, co
     a.stage_tab = reinterpret_cast<const StageDesc*>(stage_tab); a.stage_off = stage_off;
     a.dbg = getenv("PADT_MEGA_TIMELINE") ? atoi(getenv("PADT_MEGA_TIMELINE")) : 0;
     a.pf_depth = getenv("PADT_MEGA_PF") ? atoi(getenv("PADT_MEGA_PF")) : MK_DEFAULT_PF;
-    a.flags = getenv("PADT_MEGA_FLAGS") ? atoi(getenv("PADT_MEGA_FLAGS")) : MK_DEFAULT_FLAGS;
+    a.flags = decode_mega_flags();
     a.trace_layer = getenv("PADT_MEGA_TRACE_LAYER") ? atoi(getenv("PADT_MEGA_TRACE_LAYER")) : 10;
     a.pf_pace = getenv("PADT_MEGA_PF_PACE") ? atoi(getenv("PADT_MEGA_PF_PACE")) : MK_DEFAULT_PF_PACE;
     a.attn_off = decode_mega_attn_off(p);
@@ -959,8 +1019,8 @@ int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, co
     kmax = kmax > p.nh * p.hd ? kmax : p.nh * p.hd;
     a.x_ld = kmax + 8;
     // bias / residual preload covers MK_MAXGROUPS row groups per CTA in the q|k|v, o_proj and down_proj phases
-    const int qkv_groups = ((p.nh + 2 * p.nkv) * p.hd / MK_GROUP + n_sms - 1) / n_sms + 1;
-    PADT_REQUIRE(qkv_groups <= MK_MAXGROUPS && (p.D / MK_GROUP + n_sms - 1) / n_sms + 1 <= MK_MAXGROUPS,
+    const int qkv_groups = ((p.nh + 2 * p.nkv) * p.hd / MK_GROUP + n_sms - 1) / n_sms + 2;   // + 2: a shared group at either end (balanced partition)
+    PADT_REQUIRE(qkv_groups <= MK_MAXGROUPS && (p.D / MK_GROUP + n_sms - 1) / n_sms + 2 <= MK_MAXGROUPS,
                  "too many row groups per CTA for the preload buffer");
     PADT_REQUIRE(((uintptr_t)p.head & 15) == 0 && (p.protos == nullptr || ((uintptr_t)p.protos & 15) == 0), "TMA bulk copies need 16-byte aligned rows");
     static size_t configured = 0;

@@ -71,6 +71,7 @@ struct PadtHandle {
     int gen_B = 0, gen_L = 0, s_max = 0;
     bool gen_ready = false;
     int use_graph = 1;
+    int stage_tab_split = -1;        // partition mode the cached stage table was built for
     int decode_impl = 1;             // 1 = persistent kernel (decode_mega.cu) when it fits, 0 = per-layer kernels (decode.cu)
     int n_sms = 0;
     DevBuf llm_dev, gbar, stage_tab, stage_off;

@@ -29,7 +29,8 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     size_t o_h = take((size_t)B * d.D * 2), o_qkv = take((size_t)B * qkv_n * 2), o_act = take((size_t)B * act_n * 2);
     size_t o_po = take((size_t)B * d.n_heads * p.n_split * h->hd * 4), o_pml = take((size_t)B * d.n_heads * p.n_split * 2 * 4);
     size_t o_av = take((size_t)p.n_amax_blocks * B * 4), o_ai = take((size_t)p.n_amax_blocks * B * 4);
-    size_t o_cnt = take((size_t)B * d.n_kv_heads * 4 * 2), o_tok = take((size_t)B * 8);   // [B*nkv] re-armed counters (decode.cu) + [B*nkv] monotonic (decode_mega.cu)
+    size_t o_cnt = take((size_t)B * d.n_kv_heads * 4 * 2), o_tok = take((size_t)B * 8);
+    size_t o_xp = take((size_t)(h->n_sms + 1) * 64 * 8);   // [B*nkv] re-armed counters (decode.cu) + [B*nkv] monotonic (decode_mega.cu)
     bool fresh = off > h->dec_ws.bytes;
     RC(h->dec_ws.ensure(off));
     uint8_t* b = h->dec_ws.as<uint8_t>();
@@ -37,6 +38,8 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     p.part_o = (float*)(b + o_po); p.part_ml = (float*)(b + o_pml);
     p.amax_val = (float*)(b + o_av); p.amax_idx = (int*)(b + o_ai);
     p.attn_counters = (int*)(b + o_cnt); p.cur_token = (long long*)(b + o_tok);
+    p.xpart = (unsigned long long*)(b + o_xp);
+    PADT_CHECK_CUDA(cudaMemset(p.xpart, 0, (size_t)(h->n_sms + 1) * 64 * 8));   // epoch 0 = nothing published
     (void)fresh;
     PADT_CHECK_CUDA(cudaMemset(p.attn_counters, 0, (size_t)B * d.n_kv_heads * 4 * 2));
     const size_t layer_kv = (size_t)B * d.n_kv_heads * h->s_max * h->hd;
@@ -55,10 +58,13 @@ int run_step(PadtHandle* h, cudaStream_t st) {
         int sb, ns, xb;
         size_t smem;
         if (decode_mega_plan(h->dp, &sb, &ns, &xb, &smem) == 0) {
-            if (!h->stage_tab_ready) {   // the weight schedule never changes: flatten it once
+            const bool split = decode_mega_split();
+            if (!h->stage_tab_ready || h->stage_tab_split != (int)split) {   // the weight schedule only depends on the partition mode: flatten it once
                 std::vector<uint64_t> tab;
                 std::vector<int> off;
-                RC(decode_mega_build_table(h->dp, h->llm.data(), h->n_sms, tab, off));
+                RC(decode_mega_build_table(h->dp, h->llm.data(), h->n_sms, split, tab, off));
+                h->stage_tab_split = (int)split;
+                PADT_CHECK_CUDA(cudaStreamSynchronize(st));   // a previous launch may still read the old table
                 RC(h->stage_tab.ensure(tab.size() * 8 + 16));
                 RC(h->stage_off.ensure(off.size() * 4));
                 PADT_CHECK_CUDA(cudaMemcpy(h->stage_tab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));

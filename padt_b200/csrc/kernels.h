@@ -80,6 +80,7 @@ struct DecodeParams {
     bf16 *kcache, *vcache;        // [layers][B][nkv][s_max][hd]
     bf16 *h, *qkv, *act;          // [B,D], [B,(nh+2nkv)hd], [B,max(I, nh*hd)]
     float *part_o, *part_ml; int* attn_counters; int n_split;
+    unsigned long long* xpart;           // persistent kernel, balanced partition: [n_sms + 1][8][8] words {epoch, fp32 partial} of shared row groups
     float *amax_val; int *amax_idx; int n_amax_blocks;
     bf16 *last_hidden;            // [B,D] final-norm hidden of the latest forward
     bf16 *hidden_steps;           // optional [max_steps,B,D]; entry k is the state that predicted token k
@@ -101,6 +102,7 @@ int decode_mega_plan(const DecodeParams& p, int* slot_bytes, int* n_slots, int* 
 int decode_mega_nseg(int K);
 size_t decode_mega_image_elems(int n_rows, int K);
 int launch_pack_stage_image(const bf16* W, int n_rows, int K, bf16* out, cudaStream_t st);
-int decode_mega_build_table(const DecodeParams& p, const DecodeLayerW* layers_host, int G, std::vector<uint64_t>& tab, std::vector<int>& off);
+int decode_mega_build_table(const DecodeParams& p, const DecodeLayerW* layers_host, int G, bool split, std::vector<uint64_t>& tab, std::vector<int>& off);
+bool decode_mega_split();   // balanced (stage-granular) partition enabled (PADT_MEGA_FLAGS bit 128 / default)
 int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, const void* stage_tab, const int* stage_off, unsigned int* gbar,
                        int n_sms, cudaStream_t st);
