@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(NTHREADS) flash_attn_kernel(AttnParams p) {
     bf16* sK = sQ + TILE;         // [2][TILE]
     bf16* sV = sK + 2 * TILE;     // [2][TILE]
 
-    const int seg = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+    // causal: later query tiles attend over more keys -> schedule them first (CTAs are issued in blockIdx order), the short ones fill the tail
+    const int seg = blockIdx.z, h = blockIdx.y, qt = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
     const int ql = p.q_len[seg];
     if (qt * BQ >= ql) return;
     const int kl = p.k_len[seg];

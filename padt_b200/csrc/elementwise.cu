@@ -106,6 +106,39 @@ __global__ void rope_neox_f32_kernel(bf16* __restrict__ x, long long row_stride,
     p[j + half] = f2bf(ohi);
 }
 
+// same arithmetic, 8 rotation pairs per thread with 16-byte accesses (half % 8 == 0, 16-byte aligned rows)
+__global__ void rope_neox_f32_v8_kernel(bf16* __restrict__ x, long long row_stride, int n_heads, int hd, const float* __restrict__ cos,
+                                        const float* __restrict__ sin, int cs_ld, const int* __restrict__ cs_row_map, int rows) {
+    const int half = hd >> 1, cph = half >> 3;                       // 8-pair chunks per head
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)rows * n_heads * cph;
+    if (i >= total) return;
+    const int c = (int)(i % cph);
+    const int h = (int)((i / cph) % n_heads);
+    const int r = (int)(i / ((long long)cph * n_heads));
+    const int cr = cs_row_map ? cs_row_map[r] : r;
+    const float4* cp = reinterpret_cast<const float4*>(cos + (size_t)cr * cs_ld + c * 8);
+    const float4* sp = reinterpret_cast<const float4*>(sin + (size_t)cr * cs_ld + c * 8);
+    const float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    bf16* p = x + (size_t)r * row_stride + (size_t)h * hd + c * 8;
+    const uint4 lo4 = *reinterpret_cast<const uint4*>(p), hi4 = *reinterpret_cast<const uint4*>(p + half);
+    const uint32_t lo_w[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, hi_w[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+    uint32_t olo[4], ohi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 lo = bf2x_to_f2(lo_w[k]), hi = bf2x_to_f2(hi_w[k]);
+        const float a0 = __fsub_rn(__fmul_rn(lo.x, cc[2 * k]), __fmul_rn(hi.x, ss[2 * k]));
+        const float a1 = __fsub_rn(__fmul_rn(lo.y, cc[2 * k + 1]), __fmul_rn(hi.y, ss[2 * k + 1]));
+        const float b0 = __fadd_rn(__fmul_rn(hi.x, cc[2 * k]), __fmul_rn(lo.x, ss[2 * k]));
+        const float b1 = __fadd_rn(__fmul_rn(hi.y, cc[2 * k + 1]), __fmul_rn(lo.y, ss[2 * k + 1]));
+        olo[k] = f2_to_bf2x(a0, a1);
+        ohi[k] = f2_to_bf2x(b0, b1);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(olo[0], olo[1], olo[2], olo[3]);
+    *reinterpret_cast<uint4*>(p + half) = make_uint4(ohi[0], ohi[1], ohi[2], ohi[3]);
+}
+
 // cos/sin [rows, 4*quarter] fp32 = cat(rot, rot), rot = [tab[hpos], tab[wpos]]   (HF:405-409, padt.py:73-77)
 __global__ void vit_cos_sin_kernel(const float* __restrict__ tab_cos, const float* __restrict__ tab_sin, int quarter, const int* __restrict__ hpos,
                                    const int* __restrict__ wpos, float* __restrict__ cos, float* __restrict__ sin, int rows) {
@@ -254,7 +287,15 @@ int launch_copy_rows_strided(const bf16* src, long long lds, bf16* dst, long lon
 int launch_rope_neox_f32(bf16* x, long long row_stride, int n_heads, int hd, const float* cos, const float* sin, int cs_ld,
                          const int* cs_row_map, int rows, cudaStream_t st) {
     if (rows == 0) return 0;
-    long long n = (long long)rows * n_heads * (hd / 2);
+    const int half = hd / 2;
+    if (half % 8 == 0 && hd % 8 == 0 && row_stride % 8 == 0 && cs_ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)cos & 15) == 0 &&
+        ((uintptr_t)sin & 15) == 0) {
+        long long n8 = (long long)rows * n_heads * (half / 8);
+        rope_neox_f32_v8_kernel<<<nblk(n8, 256), 256, 0, st>>>(x, row_stride, n_heads, hd, cos, sin, cs_ld, cs_row_map, rows);
+        PADT_LAUNCH_CHECK();
+        return 0;
+    }
+    long long n = (long long)rows * n_heads * half;
     rope_neox_f32_kernel<<<nblk(n, 256), 256, 0, st>>>(x, row_stride, n_heads, hd, cos, sin, cs_ld, cs_row_map, rows);
     PADT_LAUNCH_CHECK();
     return 0;
