@@ -95,7 +95,9 @@ int padt_prefill(PadtHandle* h, const int64_t* input_ids, const int32_t* image_s
 int padt_decode(PadtHandle* h, int n_steps, int finish, padt_stream_t stream);
 /* Synchronises the stream and reads {tokens sampled so far, rows still unfinished}. */
 int padt_decode_status(PadtHandle* h, int32_t* n_sampled, int32_t* n_unfinished, padt_stream_t stream);
-/* Selects the decode-step implementation: 0 = per-layer kernels under one CUDA graph, 1 = same without graph. */
+/* Run-time options: "decode_impl" 1 = persistent one-launch-per-token kernel (decode_mega.cu, default; falls back to 0 when the
+ * model does not fit its shared-memory plan), 0 = per-layer kernels (decode.cu); "use_graph" 1 = replay the step from a CUDA graph
+ * (default), 0 = eager launches; "gemm_tc" 1 = persistent tcgen05 GEMM (default), 2 = one-tile tcgen05 GEMM, 0 = mma.sync GEMM. */
 int padt_set_option(PadtHandle* h, const char* name, int value);
 
 /* D1-D4: vl_decode + PaDTDecoder.forward (padt.py:342-412, padt_decoder.py:187-276).

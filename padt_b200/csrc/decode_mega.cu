@@ -1,18 +1,24 @@
 // Persistent decode-step kernel ("weight-streaming megakernel"): ONE launch per generated token.
 //
-// Organised for the HBM roofline of the step (6.27 GB per token at 3B, B=1):
-//   * grid = one CTA per SM, resident for the whole step; phases (sample | per layer: qkv, attention, o_proj, gate/up, down |
-//     logits) are separated by a grid barrier instead of kernel boundaries;
-//   * every CTA owns a fixed, contiguous slice of 8-row groups of every projection matrix, so its whole weight read
-//     schedule is known up front: a producer warp streams it with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx)
-//     into a shared-memory ring of [8 rows x Kseg] stages, running AHEAD across phase boundaries (while the consumers sit in
-//     a grid barrier or in the attention phase the ring keeps filling);
-//   * all 16 consumer warps work on the SAME stage, each on its own slice of the K columns: ldmatrix (rows padded by 16 B ->
-//     conflict free) + mma.sync m16n8k16 with the weights as the B operand (n = 8 weight rows) and the activation rows as the
-//     A operand (m = batch row, <= 8 real rows); a stage is therefore consumed and released in ~100 cycles, so the ring
-//     pipeline never drains, and the CUDA cores only run the tiny cross-warp reduction + epilogue per row group.
-// Arithmetic: bf16 products accumulated in fp32 by the tensor core, partial sums of the 16 K-slices added in a fixed order,
-// then the HF rounding points (bias add / residual add / SiLU*up / logit -> bf16) exactly as in decode.cu.
+// Organised for the HBM roofline of the step (6.27 GB per token at 3B, B=1); DESIGN.md §4.1 has the measurements.
+//   * grid = one CTA per SM, resident for the whole step: 16 tensor-core consumer warps, 1 epilogue warp, 1 TMA producer warp,
+//     1 L2 prefetch warp.  Phases (sample | per layer: qkv, attention, o_proj, gate/up, down | head rows | prototype rows) run in
+//     ONE phase loop and are separated by a grid barrier instead of kernel boundaries;
+//   * every CTA owns a fixed slice of every projection matrix, so its whole weight read schedule is known up front (a host-built
+//     descriptor table): producer lane l streams the stages of ring slot l with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//     complete_tx, L2 evict_first) into a shared-memory ring of [8 rows x Kseg] stages, gated only by free slots, i.e. running
+//     AHEAD across phase boundaries; the prefetch warp walks the same table further ahead and pulls stages into L2, so the stream
+//     continues while the consumers sit in a grid barrier or in the attention phase and the ring is full;
+//   * two half-CTAs of 8 warps alternate over the stages (the ring has an EVEN slot count, so a slot always belongs to one half);
+//     inside a stage every warp owns a K slice: ldmatrix.x4 on the padded stage (conflict free) + mma.sync m16n8k16 with the
+//     weights as the B operand (n = 8 weight rows) and the batch rows as the A operand (<= 8 real rows).  Shared-memory addresses
+//     are computed once per phase and the activation fragments of K = 2048 phases stay in registers, so a stage costs
+//     4 x (LDSM.x4 + 2 HMMA) per warp; the epilogue warp adds the 16 K-slice partials of a row group in fixed order and applies
+//     the HF rounding points (bias add / residual add / SiLU*up / bf16 logit + masked arg-max) exactly as decode.cu does;
+//   * attention: (row, kv head, split) items; the item's K/V tile is copied to shared memory BEFORE the barrier that publishes
+//     q/k/v; the CTAs of a kv head meet on a monotonic counter and each combines a slice of the outputs over all splits;
+//   * down_proj is distributed by stages, not row groups (balanced); a row group shared by two CTAs is completed by the CTA that
+//     owns its first K segments from the neighbour's published fp32 partial ({epoch, value} words, fixed order).
 // Replaces the per-token body of _sample_vision_token / forward_main (padt.py:671-757, 221-229, 268-301).
 #include "common.cuh"
 #include "kernels.h"
@@ -40,14 +46,12 @@ struct MegaArgs {
     DecodeParams p;
     const DecodeLayerW* layers;   // device copy
     unsigned int* gbar;           // grid barrier counter, zeroed by a memset node before every launch
-    int slot_bytes, n_slots, x_bytes, x_ld;
+    int slot_bytes, n_slots, x_bytes;
     const struct StageDesc* stage_tab;   // [sum stages] descriptors, CTA c owns [stage_off[c], stage_off[c+1])
     const int* stage_off;
-    int dbg;                      // PADT_MEGA_TIMELINE bits: 1 print cycle breakdown, 2 no compute, 4 no grid barrier, 8 no attention,
-                                  //   16 per-phase timeline of layer `trace_layer`
+    int dbg;                      // PADT_MEGA_TIMELINE bits: 1 print cycle breakdown, 2 no epilogue / mma, 4 no grid barrier, 8 no attention, 64 no mma
     int pf_depth;                 // L2 prefetch warp: stages kept in flight towards L2 beyond the ring (0 = off)
     int flags;                    // MF_* bits
-    int trace_layer;
     int pf_pace;                  // minimum cycles between two stage prefetches (keeps the request queues short during a stall)
     int attn_off;                 // byte offset of the attention scratch inside the activation region
 };
@@ -1006,7 +1010,6 @@ int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, co
     a.dbg = getenv("PADT_MEGA_TIMELINE") ? atoi(getenv("PADT_MEGA_TIMELINE")) : 0;
     a.pf_depth = getenv("PADT_MEGA_PF") ? atoi(getenv("PADT_MEGA_PF")) : MK_DEFAULT_PF;
     a.flags = decode_mega_flags();
-    a.trace_layer = getenv("PADT_MEGA_TRACE_LAYER") ? atoi(getenv("PADT_MEGA_TRACE_LAYER")) : 10;
     a.pf_pace = getenv("PADT_MEGA_PF_PACE") ? atoi(getenv("PADT_MEGA_PF_PACE")) : MK_DEFAULT_PF_PACE;
     a.attn_off = decode_mega_attn_off(p);
     PADT_REQUIRE(p.n_split * p.nkv * p.B <= n_sms, "one attention item per CTA");
@@ -1015,9 +1018,6 @@ int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, co
         padt_set_error("persistent decode kernel: configuration does not fit in shared memory");
         return -1;
     }
-    int kmax = p.I > p.D ? p.I : p.D;
-    kmax = kmax > p.nh * p.hd ? kmax : p.nh * p.hd;
-    a.x_ld = kmax + 8;
     // bias / residual preload covers MK_MAXGROUPS row groups per CTA in the q|k|v, o_proj and down_proj phases
     const int qkv_groups = ((p.nh + 2 * p.nkv) * p.hd / MK_GROUP + n_sms - 1) / n_sms + 2;   // + 2: a shared group at either end (balanced partition)
     PADT_REQUIRE(qkv_groups <= MK_MAXGROUPS && (p.D / MK_GROUP + n_sms - 1) / n_sms + 2 <= MK_MAXGROUPS,

@@ -225,8 +225,9 @@ def test_persistent_decode_kernel_matches_per_layer_kernels(name):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("dims", [dict(D=3584, I=18944, nh=28, nkv=4), dict(D=2048, I=18944, nh=16, nkv=2), dict(D=3584, I=11008, nh=28, nkv=4)],
-                         ids=["7B_dims", "3B_I18944", "7B_I11008"])
+@pytest.mark.parametrize("dims", [dict(D=3584, I=18944, nh=28, nkv=4), dict(D=2048, I=18944, nh=16, nkv=2), dict(D=3584, I=11008, nh=28, nkv=4),
+                                  dict(D=2048, I=11008, nh=16, nkv=2, B=3)],
+                         ids=["7B_dims", "3B_I18944", "7B_I11008", "3B_dims_batch3"])
 def test_persistent_decode_kernel_at_7b_projection_shapes(dims):
     """PaDT_Pro_7B projection shapes (2 layers, small vocabulary so the weights stay below 2 GB): K = 18944 needs 16 ring stages per
     row group and 19 KB stages, K = 3584 four stages -- different stage / slot geometry than 3B.  Regression test for the odd
@@ -243,15 +244,16 @@ def test_persistent_decode_kernel_at_7b_projection_shapes(dims):
     model = PaDTForConditionalGeneration.from_random(cfg, seed=3, device="cuda:0")
     side = 24
     P = side * side
+    nb = dims.get("B", 1)           # rows per GPU (the shared-row-group exchange of the balanced down_proj partition carries all rows)
     g = torch.Generator().manual_seed(5)
-    pv = torch.randn((P, cfg.vision.patch_dim), generator=g).to(torch.bfloat16).cuda()
+    pv = torch.randn((nb * P, cfg.vision.patch_dim), generator=g).to(torch.bfloat16).cuda()
     M = P // 4
-    row = torch.randint(0, vocab - 20, (14,), generator=g).tolist() + [cfg.vision_start_token_id] + [cfg.image_token_id] * M + \
-        [cfg.vision_end_token_id] + torch.randint(0, vocab - 20, (30,), generator=g).tolist()
-    ids = torch.tensor([row]).cuda()
+    rows = [torch.randint(0, vocab - 20, (14,), generator=g).tolist() + [cfg.vision_start_token_id] + [cfg.image_token_id] * M +
+            [cfg.vision_end_token_id] + torch.randint(0, vocab - 20, (30,), generator=g).tolist() for _ in range(nb)]
+    ids = torch.tensor(rows).cuda()
     steps = 6
-    forced = torch.randint(0, vocab - 20, (1, steps), generator=g).cuda()     # teacher forcing keeps the three runs on the same inputs
-    kw = dict(input_ids=ids, attention_mask=torch.ones_like(ids), pixel_values=pv, image_grid_thw=torch.tensor([[1, side, side]]).cuda(),
+    forced = torch.randint(0, vocab - 20, (nb, steps), generator=g).cuda()     # teacher forcing keeps the three runs on the same inputs
+    kw = dict(input_ids=ids, attention_mask=torch.ones_like(ids), pixel_values=pv, image_grid_thw=torch.tensor([[1, side, side]] * nb).cuda(),
               max_new_tokens=steps, return_dict_in_generate=True, eos_token_id=[], output_hidden_states=True, forced_tokens=forced)
     outs = {}
     for impl, graph in ((0, 0), (1, 0), (1, 1)):
