@@ -8,6 +8,7 @@
 // row per thread), apply bias / GELU / residual / interleaved SwiGLU and store bf16 rows.
 // Replaces the cuBLAS calls behind every nn.Linear of the reference's tensor-core-bound stages.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -403,10 +404,15 @@ int launch_bn(const GemmParams& p, cudaStream_t st) {
     return 0;
 }
 
+// Tile width: 256 columns whenever N allows.  Measured (profiles/r01b/call38_gemm_bn_heuristic.log): switching to 128-column tiles
+// where they shorten the tile-round count (e.g. M = 2350, N = 2048: 152 tiles of 256 columns on 148 SMs = 2 rounds vs 304 tiles of
+// 128 = 1.5 rounds) is SLOWER (down_proj 137 -> 159 us): the narrower tile moves 1.33x the operand bytes per flop through L2.
+// PADT_GEMM_BN=128 forces the narrow tile for measurements.
 template <int EPI>
 int launch_epi(const GemmParams& p, cudaStream_t st) {
-    if (p.N >= 256) return launch_bn<256, EPI>(p, st);
-    return launch_bn<128, EPI>(p, st);
+    static const int forced = getenv("PADT_GEMM_BN") ? atoi(getenv("PADT_GEMM_BN")) : 0;
+    if (p.N < 256 || forced == 128) return launch_bn<128, EPI>(p, st);
+    return launch_bn<256, EPI>(p, st);
 }
 
 }  // namespace
