@@ -119,6 +119,12 @@ int padt_op_attention(const void* q, const void* k, const void* v, void* o, int6
 int padt_op_rope_neox(void* x, int64_t row_stride, int n_heads, int head_dim, const float* cos, const float* sin, int cs_ld, int rows,
                       padt_stream_t stream);
 
+/* Host-only planning helpers of the persistent decode kernel (no device work; CPU tests): shared-memory plan
+ * out4 = {slot_bytes, n_slots (always even), activation-region bytes, dynamic shared memory bytes}; stage range of one CTA for an
+ * [n_rows, K] matrix: out3 = {K segments per row group, first stage, one-past-last stage}, stage = row_group * nseg + segment. */
+int padt_debug_mega_plan(int D, int I, int n_heads, int n_kv_heads, int B, int32_t* out4);
+int padt_debug_mega_partition(int n_rows, int K, int n_ctas, int balanced, int cta, int32_t* out3);
+
 #ifdef __cplusplus
 }
 #endif

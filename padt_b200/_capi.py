@@ -44,6 +44,7 @@ EXPORTED_SYMBOLS = (
     "padt_last_error", "padt_version", "padt_launch_count", "padt_weight_count", "padt_weight_name", "padt_create", "padt_destroy",
     "padt_vit_plan_host", "padt_vit_forward", "padt_prototypes", "padt_prefill", "padt_decode", "padt_decode_status", "padt_set_option",
     "padt_vl_decode", "padt_op_gemm", "padt_op_rmsnorm", "padt_op_attention", "padt_op_rope_neox",
+    "padt_debug_mega_plan", "padt_debug_mega_partition",
 )
 
 

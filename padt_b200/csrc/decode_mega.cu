@@ -960,23 +960,29 @@ int decode_mega_plan(const DecodeParams& p, int* slot_bytes, int* n_slots, int* 
 }
 
 // Host mirror of make_seg/layer_seg: flattens the image-backed stages of every CTA (same order as the consumers walk them).
+// Stage range [lo, hi) of CTA `c` for a matrix of n_rows x K (stage = row group * nseg + K segment); host mirror of make_seg.
+void decode_mega_stage_range(int n_rows, int K, int G, bool balanced, int c, int* nseg_out, unsigned int* lo, unsigned int* hi) {
+    const int nseg = decode_mega_nseg(K);
+    const unsigned int groups = (unsigned int)(n_rows + MK_GROUP - 1) / MK_GROUP;
+    if (balanced && groups >= (unsigned int)G) {
+        const unsigned int S = groups * (unsigned int)nseg;
+        *lo = (S * (unsigned int)c) / (unsigned int)G; *hi = (S * (unsigned int)(c + 1)) / (unsigned int)G;
+    } else {
+        *lo = ((groups * (unsigned int)c) / (unsigned int)G) * nseg; *hi = ((groups * (unsigned int)(c + 1)) / (unsigned int)G) * nseg;
+    }
+    *nseg_out = nseg;
+}
+
 int decode_mega_build_table(const DecodeParams& p, const DecodeLayerW* layers_host, int G, bool split, std::vector<uint64_t>& tab, std::vector<int>& off) {
     tab.clear();
     off.assign(G + 1, 0);
     for (int c = 0; c < G; ++c) {
         off[c] = (int)(tab.size() / 2);
         auto emit = [&](const bf16* img, int n_rows, int K, bool balanced) {
-            const int nseg = decode_mega_nseg(K);
-            const int Kseg = K / nseg;
-            const unsigned int groups = (unsigned int)(n_rows + MK_GROUP - 1) / MK_GROUP;
-            unsigned int lo, hi;                       // stage range, same arithmetic as make_seg
-            if (balanced && groups >= (unsigned int)G) {
-                const unsigned int S = groups * (unsigned int)nseg;
-                lo = (S * (unsigned int)c) / (unsigned int)G; hi = (S * (unsigned int)(c + 1)) / (unsigned int)G;
-            } else {
-                lo = ((groups * (unsigned int)c) / (unsigned int)G) * nseg; hi = ((groups * (unsigned int)(c + 1)) / (unsigned int)G) * nseg;
-            }
-            const uint32_t bytes = MK_GROUP * ((uint32_t)Kseg * 2 + 16);
+            int nseg;
+            unsigned int lo, hi;
+            decode_mega_stage_range(n_rows, K, G, balanced, c, &nseg, &lo, &hi);
+            const uint32_t bytes = MK_GROUP * ((uint32_t)(K / nseg) * 2 + 16);
             for (unsigned int st = lo; st < hi; ++st) {
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(img) + (size_t)st * bytes;
                 tab.push_back((uint64_t)(uintptr_t)src);

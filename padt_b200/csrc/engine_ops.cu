@@ -27,3 +27,24 @@ extern "C" int padt_op_rope_neox(void* x, int64_t row_stride, int n_heads, int h
                                  padt_stream_t stream) {
     return launch_rope_neox_f32((bf16*)x, row_stride, n_heads, head_dim, cos, sin, cs_ld, nullptr, rows, (cudaStream_t)stream);
 }
+
+// ---- host-only planning helpers of the persistent decode kernel (no device work; used by the CPU tests)
+extern "C" int padt_debug_mega_plan(int D, int I, int n_heads, int n_kv_heads, int B, int32_t* out4) {
+    PADT_REQUIRE(out4 && n_heads > 0 && D % n_heads == 0, "arguments");
+    DecodeParams p = {};
+    p.B = B; p.D = D; p.I = I; p.nh = n_heads; p.nkv = n_kv_heads; p.hd = D / n_heads;
+    int sb = 0, ns = 0, xb = 0;
+    size_t smem = 0;
+    if (decode_mega_plan(p, &sb, &ns, &xb, &smem)) { padt_set_error("model does not fit the shared-memory plan"); return -1; }
+    out4[0] = sb; out4[1] = ns; out4[2] = xb; out4[3] = (int32_t)smem;
+    return 0;
+}
+
+extern "C" int padt_debug_mega_partition(int n_rows, int K, int n_ctas, int balanced, int cta, int32_t* out3) {
+    PADT_REQUIRE(out3 && n_ctas > 0 && cta >= 0 && cta < n_ctas && K % 16 == 0, "arguments");
+    int nseg;
+    unsigned int lo, hi;
+    decode_mega_stage_range(n_rows, K, n_ctas, balanced != 0, cta, &nseg, &lo, &hi);
+    out3[0] = nseg; out3[1] = (int32_t)lo; out3[2] = (int32_t)hi;
+    return 0;
+}

@@ -103,6 +103,7 @@ int decode_mega_nseg(int K);
 size_t decode_mega_image_elems(int n_rows, int K);
 int launch_pack_stage_image(const bf16* W, int n_rows, int K, bf16* out, cudaStream_t st);
 int decode_mega_build_table(const DecodeParams& p, const DecodeLayerW* layers_host, int G, bool split, std::vector<uint64_t>& tab, std::vector<int>& off);
+void decode_mega_stage_range(int n_rows, int K, int G, bool balanced, int c, int* nseg, unsigned int* lo, unsigned int* hi);
 bool decode_mega_split();   // balanced (stage-granular) partition enabled (PADT_MEGA_FLAGS bit 128 / default)
 int launch_decode_mega(const DecodeParams& p, const DecodeLayerW* layers_dev, const void* stage_tab, const int* stage_off, unsigned int* gbar,
                        int n_sms, cudaStream_t st);

@@ -1,0 +1,93 @@
+"""CPU: host-side planning of the persistent decode kernel (csrc/decode_mega.cu) through the C ABI -- no device work.
+
+* shared-memory plan: fits 227 KB, ring has an EVEN number of slots (an odd ring broke PaDT_Pro_7B: the two half-CTAs take
+  alternate stages and only wait on their own stages' barriers), one slot holds the largest stage of the model;
+* stage partition: the 148 per-CTA stage ranges tile [0, groups * nseg) exactly once, group-aligned without the balanced mode,
+  sizes within one stage of each other with it, and every balanced range holds at least one whole group's worth of stages
+  (so a row group is shared by at most two CTAs -- the head/tail combine in the epilogue relies on it)."""
+import ctypes as C
+
+import pytest
+
+from padt_b200 import _capi
+
+MODELS = {
+    "PaDT_Pro_3B": dict(D=2048, I=11008, nh=16, nkv=2, vocab=151936),
+    "PaDT_Pro_7B": dict(D=3584, I=18944, nh=28, nkv=4, vocab=152064),
+    "small": dict(D=1024, I=2752, nh=8, nkv=2, vocab=4096),
+    "tiny": dict(D=256, I=640, nh=2, nkv=1, vocab=512),
+}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    lib = _capi.load()
+    lib.padt_debug_mega_plan.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int32)]
+    lib.padt_debug_mega_partition.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int32)]
+    return lib
+
+
+def _plan(lib, m, B):
+    out = (C.c_int32 * 4)()
+    rc = lib.padt_debug_mega_plan(m["D"], m["I"], m["nh"], m["nkv"], B, out)
+    return rc, list(out)
+
+
+def _nseg_and_stage_bytes(lib, K):
+    out = (C.c_int32 * 3)()
+    assert lib.padt_debug_mega_partition(8, K, 1, 0, 0, out) == 0
+    nseg = out[0]
+    return nseg, 8 * ((K // nseg) * 2 + 16)
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+@pytest.mark.parametrize("B", [1, 2, 4])
+def test_shared_memory_plan(lib, name, B):
+    m = MODELS[name]
+    rc, (slot_bytes, n_slots, x_bytes, smem) = _plan(lib, m, B)
+    if (name, B) == ("PaDT_Pro_7B", 4):
+        # 4 rows x 18952 bf16 of down_proj activations (152 KB) leave no room for a 4-slot ring: the engine then runs the
+        # per-layer kernels (decode.cu) for this batch size -- the plan must say so instead of producing a tiny ring
+        assert rc != 0
+        return
+    assert rc == 0
+    assert n_slots % 2 == 0 and n_slots >= 4, "the ring must have an even number of slots"
+    assert smem <= 227 * 1024 - 4 * 1024, "dynamic + ~3.5 KB static shared memory must fit one SM"
+    assert slot_bytes % 128 == 0
+    for K in (m["D"], m["nh"] * 128, m["I"]):
+        nseg, stage_bytes = _nseg_and_stage_bytes(lib, K)
+        assert K % (16 * nseg) == 0 and stage_bytes <= slot_bytes
+    kmax = max(m["D"], m["I"])
+    assert x_bytes >= B * (kmax + 8) * 2, "activation rows of the widest phase"
+    assert x_bytes >= B * (m["D"] + 8) * 2 + 2 * 64 * 136 * 2, "K/V tiles sit behind the q/k/v activation rows"
+
+
+@pytest.mark.parametrize("name", ["PaDT_Pro_3B", "PaDT_Pro_7B", "small"])
+@pytest.mark.parametrize("balanced", [0, 1])
+def test_stage_partition_tiles_every_matrix(lib, name, balanced):
+    m = MODELS[name]
+    G = 148
+    qkv_n = (m["nh"] + 2 * m["nkv"]) * 128
+    for n_rows, K in ((qkv_n, m["D"]), (m["D"], m["nh"] * 128), (2 * m["I"], m["D"]), (m["D"], m["I"]), (m["vocab"], m["D"])):
+        out = (C.c_int32 * 3)()
+        groups = (n_rows + 7) // 8
+        prev_hi, sizes, nseg = 0, [], None
+        for c in range(G):
+            assert lib.padt_debug_mega_partition(n_rows, K, G, balanced, c, out) == 0
+            nseg, lo, hi = out[0], out[1], out[2]
+            assert lo == prev_hi and hi >= lo
+            prev_hi = hi
+            sizes.append(hi - lo)
+            if not (balanced and groups >= G):
+                assert lo % nseg == 0 and hi % nseg == 0, "group-aligned partition"
+        assert prev_hi == groups * nseg, "ranges must cover every stage exactly once"
+        if balanced and groups >= G:
+            assert max(sizes) - min(sizes) <= 1
+            assert min(sizes) >= nseg, "a row group may be shared by at most two CTAs"
+        else:
+            assert max(sizes) - min(sizes) <= nseg
+
+
+def test_plan_rejects_models_that_do_not_fit(lib):
+    rc, _ = _plan(lib, dict(D=2048, I=11008, nh=16, nkv=2), 9)      # > 8 rows per GPU
+    assert rc != 0
