@@ -217,6 +217,21 @@ __device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split
         sQ[g * DA_HD + j + 64] = rbf(rbf(hi * c) + rbf(lo * sn));
     }
     const bool owns_new = (cur >= k_begin && cur < k_end);
+    // the split that owns the key of this step loads its raw k / v (and rotary factors) together with the queries, so that
+    // the append below does not add a dependent global round trip after the K/V tile wait (every other split of the kv head
+    // waits for this one before the partials can be combined)
+    const bf16* kn = row + (size_t)(a.nh + kvh) * DA_HD;
+    const bf16* vn = row + (size_t)(a.nh + a.nkv + kvh) * DA_HD;
+    float nk_lo = 0.f, nk_hi = 0.f, nk_c = 0.f, nk_s = 0.f;
+    bf16 nv = f2bf(0.f);
+    if (owns_new) {
+        if (tid < 64) {
+            nk_c = bf2f(a.cos_tab[(size_t)pos * 64 + tid]); nk_s = bf2f(a.sin_tab[(size_t)pos * 64 + tid]);
+            nk_lo = bf2f(kn[tid]); nk_hi = bf2f(kn[tid + 64]);
+        } else if (tid < 192) {
+            nv = vn[tid - 64];
+        }
+    }
 
     float m_run = -INFINITY, l_run = 0.f;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -228,20 +243,15 @@ __device__ __forceinline__ void decode_attn_body(const DecAttnArgs& a, int split
         if (owns_new && cur >= t0 && cur < t0 + DA_TILE) {
             // new key/value of this step: rope k in bf16 semantics, append to the cache, and use it from smem
             int r = cur - t0;
-            const bf16* kn = row + (size_t)(a.nh + kvh) * DA_HD;
-            const bf16* vn = row + (size_t)(a.nh + a.nkv + kvh) * DA_HD;
             if (tid < 64) {
                 int j = tid;
-                float c = bf2f(a.cos_tab[(size_t)pos * 64 + j]), sn = bf2f(a.sin_tab[(size_t)pos * 64 + j]);
-                float lo = bf2f(kn[j]), hi = bf2f(kn[j + 64]);
-                bf16 olo = f2bf(rbf(lo * c) + rbf(-hi * sn)), ohi = f2bf(rbf(hi * c) + rbf(lo * sn));
+                bf16 olo = f2bf(rbf(nk_lo * nk_c) + rbf(-nk_hi * nk_s)), ohi = f2bf(rbf(nk_hi * nk_c) + rbf(nk_lo * nk_s));
                 sK[r * DA_LD + j] = olo; sK[r * DA_LD + j + 64] = ohi;
                 kc[(size_t)cur * DA_HD + j] = olo; kc[(size_t)cur * DA_HD + j + 64] = ohi;
             } else if (tid < 192) {
                 int j = tid - 64;
-                bf16 v = vn[j];
-                sV[r * DA_LD + j] = v;
-                vc[(size_t)cur * DA_HD + j] = v;
+                sV[r * DA_LD + j] = nv;
+                vc[(size_t)cur * DA_HD + j] = nv;
             }
             sync();
         }

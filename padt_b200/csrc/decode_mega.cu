@@ -798,8 +798,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(MegaArgs a) 
             if (has_item) {
                 if (tid == 0) WD_MARK(g_wd_sub, 3);
                 decode_attn_body<false>(attn_args(li), a_split, a_kvh, a_b, attn_smem, tid, MK_STHREADS, CSync(), kv_in_flight);
-                __threadfence();
-                CSync()();
+                CSync()();      // orders the partial stores of all warps before thread 0's gpu-scope release below (as in grid_sync)
                 if (tid == 0) WD_MARK(g_wd_sub, 4);
                 if (tid == 0) {
                     unsigned int* cnt = reinterpret_cast<unsigned int*>(p.attn_counters) + p.B * p.nkv + a_b * p.nkv + a_kvh;   // monotonic counters
