@@ -101,3 +101,22 @@ def test_vit_plan_matches_oracle(lib):
         inv = 1.0 / (10000.0 ** (torch.arange(0, 40, 2, dtype=torch.float) / 40))
         mine = torch.cat([torch.outer(torch.tensor(hp, dtype=torch.float), inv), torch.outer(torch.tensor(wp, dtype=torch.float), inv)], dim=1)
         assert torch.equal(rot, mine)
+
+
+def test_bench_workload_constants_match_the_design():
+    """bench.py's algorithmic bytes per decode step (the roofline numerator) and prompt builder: DESIGN.md §4 / SURVEY.md §8d."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from padt_b200.config import PRESETS
+    c3, c7 = PRESETS["PaDT_Pro_3B"](), PRESETS["PaDT_Pro_7B"]()
+    b3 = bench.decode_bytes_per_step(c3, 2304, 2350 + 128)
+    assert abs(b3 - 6.27e9) < 0.01e9, b3                      # 3B, B=1, 1344 px: 6.27 GB per token
+    layer_params = (b3 - 2 * 151936 * 2048 - 2 * 2304 * 2048 - (2478 + 1) * 36864) / 2
+    assert abs(layer_params - 2.7748e9) < 1e6                 # SURVEY.md §8d: 2.7748 B layer parameters
+    b7 = bench.decode_bytes_per_step(c7, 2304, 2350 + 128)
+    assert abs(b7 - 14.30e9) < 0.02e9, b7                     # 7B: 14.30 GB per token
+    ids = bench.build_prompt(c3, bench.L_PROMPT, 2304, seed=100)
+    assert ids.shape == (1, 2350) and int((ids == c3.image_token_id).sum()) == 2304
+    assert int(ids[0, 14]) == c3.vision_start_token_id and int(ids[0, 14 + 1 + 2304]) == c3.vision_end_token_id
