@@ -15,6 +15,9 @@ padt.py:671-757 because the copied HF-4.50 ``generate`` cannot run on transforme
 import os
 import sys
 
+# same oneDNN kernel family as the tests (tests/conftest.py): bit-exactness of bf16 GEMMs depends on the ISA path
+os.environ.setdefault("ONEDNN_MAX_CPU_ISA", "AVX512_CORE")
+
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -24,7 +27,7 @@ sys.path.insert(0, HERE)
 
 import ref_shim  # noqa: E402
 import padt_oracle as O  # noqa: E402
-from padt_b200.config import padt_tiny  # noqa: E402
+from padt_b200.config import padt_small, padt_tiny  # noqa: E402
 from padt_b200.weights import random_weights  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -250,10 +253,17 @@ def case(name, cfg, wseed, grids, prompt_lens, steps, iseed, objects):
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(min(8, os.cpu_count() or 1))
+    only = sys.argv[1:]                     # optional: names of the cases to (re)generate
     # B=1, tied head, ragged windows (grid 8x12 -> merged 4x6: windows of 16 and 8 merged units)
-    case("tiny_b1", padt_tiny(tie=True), 0, [(1, 8, 12)], [9], 12, 1, [[(2, 3), (7, 2)]])
+    if not only or "tiny_b1" in only:
+        case("tiny_b1", padt_tiny(tie=True), 0, [(1, 8, 12)], [9], 12, 1, [[(2, 3), (7, 2)]])
     # B=2, left padded, two different grids, untied head
-    case("tiny_b2", padt_tiny(tie=False), 1, [(1, 8, 12), (1, 4, 8)], [5, 11], 10, 2, [[(1, 2)], [(3, 1), (5, 3)]])
+    if not only or "tiny_b2" in only:
+        case("tiny_b2", padt_tiny(tie=False), 1, [(1, 8, 12), (1, 4, 8)], [5, 11], 10, 2, [[(1, 2)], [(3, 1), (5, 3)]])
+    # mid-size: GQA group 4, 4 LLM layers, 6 ViT blocks (two full-attention), untied head, two rows with different grids incl. a
+    # window-divisible side (16 patches = 2 windows of 8 -> the empty pad window of get_window_index), left padded
+    if not only or "small_b2" in only:
+        case("small_b2", padt_small(tie=False), 2, [(1, 12, 16), (1, 8, 8)], [7, 4], 8, 3, [[(1, 3)], [(2, 2), (5, 2)]])
 
 
 if __name__ == "__main__":

@@ -371,7 +371,9 @@ def prefill(w: W, cfg, input_ids: Tensor, attention_mask: Tensor, pixel_values: 
     position_ids, rope_deltas = get_rope_index(cfg, input_ids, image_grid_thw, attention_mask)
     cache = KVCache(cfg.text.num_layers)
     hidden = llm_forward(w, cfg, x, position_ids, attention_mask, cache)
-    logits_last = extended_logits(w, cfg, hidden[:, -1:, :], protos, logit_mask)[:, -1, :]
+    # the reference projects EVERY prompt position (padt.py:292-301, no logits_to_keep); restating that, rather than only the last
+    # row, also keeps the CPU GEMM shape -- and therefore oneDNN's summation order -- identical to the reference's
+    logits_last = extended_logits(w, cfg, hidden, protos, logit_mask)[:, -1, :]
     return dict(image_embeds=image_embeds, high_res=high_res, visual_pe=pe, prototypes=protos, logit_mask=logit_mask,
                 position_ids=position_ids, rope_deltas=rope_deltas, cache=cache, hidden=hidden, logits_last=logits_last)
 

@@ -6,7 +6,7 @@ import torch
 
 import padt_oracle as O
 from helpers import load_golden
-from padt_b200.config import padt_tiny
+from padt_b200.config import padt_small, padt_tiny
 from padt_b200.weights import random_weights
 
 
@@ -14,10 +14,14 @@ def _eq(a, b):
     return bool(((a == b) | (torch.isinf(a.float()) & torch.isinf(b.float()))).all()) and a.shape == b.shape
 
 
-@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+def _cfg(fx):
+    return padt_small(tie=fx["tie"]) if fx["cfg_name"] == "PaDT_small" else padt_tiny(tie=fx["tie"], vocab=fx["vocab"])
+
+
+@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2", "small_b2"])
 def test_oracle_reproduces_reference(name):
     fx = load_golden(name)
-    cfg = padt_tiny(tie=fx["tie"], vocab=fx["vocab"])
+    cfg = _cfg(fx)
     w = random_weights(cfg, seed=fx["wseed"])
     with torch.no_grad():
         emb, high, (cos, sin) = O.vit_forward(w, cfg, fx["pixel_values"], fx["grid"])
