@@ -23,11 +23,9 @@ ap.add_argument("--out", default="gpurun_out/mega_sweep.jsonl")
 ap.add_argument("--lib", default="", help="load this build of the library instead of padt_b200/libpadt_b200.so (A/B runs)")
 a = ap.parse_args()
 
-DEFAULT = [(0, 0, 0), (0, 2, 0), (0, 4, 0), (0, 6, 0), (0, 7, 0),
-           (4, 6, 0), (8, 6, 0), (16, 6, 0), (32, 6, 0),
-           (8, 7, 0), (16, 7, 0), (32, 7, 0), (48, 7, 0),
-           (16, 7, 400), (16, 7, 800), (32, 7, 400), (32, 7, 800),
-           (16, 14, 0), (16, 15, 0), (32, 15, 0), (16, 15, 800), (32, 15, 800)]
+# (prefetch depth in stages, PADT_MEGA_FLAGS bit mask, prefetch pace in cycles); flags: 1 evict_first, 2 no register-resident
+# activations, 4 K/V tile prefetch, 8 per-line L2 prefetch, 16 evict_last prefetch, 64 minimal-traffic staging, 128 balanced down_proj
+DEFAULT = [(16, 205, 0), (0, 205, 0), (8, 205, 0), (24, 205, 0), (16, 77, 0), (16, 141, 0), (16, 201, 0), (16, 204, 0), (16, 207, 0), (16, 197, 0)]
 
 
 def parse_cfgs(s):
