@@ -23,8 +23,11 @@ def _model(cfg, seed):
 
 
 def _cfg_for(fx):
-    from padt_b200.config import padt_tiny
-    return padt_tiny(tie=fx["tie"], vocab=fx["vocab"])
+    from padt_b200.config import padt_small, padt_tiny
+    return padt_small(tie=fx["tie"]) if fx["cfg_name"] == "PaDT_small" else padt_tiny(tie=fx["tie"], vocab=fx["vocab"])
+
+
+GOLDEN = ["tiny_b1", "tiny_b2", "small_b2"]
 
 
 def _assert_box_like(a, b, what):
@@ -34,7 +37,7 @@ def _assert_box_like(a, b, what):
     assert bool((d <= tol).all()), f"{what}: max abs diff {float(d.max())}, worst tol {float(tol.max())}, n>1e-3: {int((d > 1e-3).sum())}/{d.numel()}"
 
 
-@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+@pytest.mark.parametrize("name", GOLDEN)
 def test_vit_against_reference_golden(name):
     fx = load_golden(name)
     model, _ = _model(_cfg_for(fx), fx["wseed"])
@@ -48,7 +51,7 @@ def test_vit_against_reference_golden(name):
     assert_close_bf16(protos, fx["prototypes"], "prototypes")
 
 
-@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+@pytest.mark.parametrize("name", GOLDEN)
 def test_generate_against_reference_golden(name):
     fx = load_golden(name)
     model, _ = _model(_cfg_for(fx), fx["wseed"])
@@ -75,7 +78,7 @@ def test_generate_against_reference_golden(name):
     assert out.past_logit_mask.shape == (fx["input_ids"].shape[0], fx["vocab"] + fx["prototypes"].shape[0])
 
 
-@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+@pytest.mark.parametrize("name", GOLDEN)
 def test_teacher_forced_against_reference_golden(name):
     """Feeds the reference's forced token stream (half of it VRT ids of the row's own image) and compares, per step, the
     arg-max and the final-norm hidden state with what the reference produced."""
@@ -93,7 +96,7 @@ def test_teacher_forced_against_reference_golden(name):
         assert_close_bf16(out.hidden_states[s][-1][:, 0, :], fx["forced_last_hidden"][s], f"hidden step {s}")
 
 
-@pytest.mark.parametrize("name", ["tiny_b1", "tiny_b2"])
+@pytest.mark.parametrize("name", GOLDEN)
 def test_vl_decode_against_reference_golden(name):
     fx = load_golden(name)
     model, _ = _model(_cfg_for(fx), fx["wseed"])
