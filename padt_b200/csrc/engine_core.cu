@@ -254,6 +254,12 @@ extern "C" int padt_set_option(PadtHandle* h, const char* name, int value) {
     if (n == "use_graph") { h->use_graph = value; return 0; }
     if (n == "gemm_tc") { g_padt_gemm_tc = value; return 0; }
     if (n == "decode_impl") {
+        if (h->decode_impl != value) {
+            // the persistent kernel's split-KV and shared-row-group counters are epochs counted in ITS launches since the prefill:
+            // switching implementation in the middle of a generation would wait for epochs that never come.  Make the next
+            // padt_decode fail loudly ("padt_prefill must run first") instead.
+            h->gen_ready = false;
+        }
         h->decode_impl = value;
         if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
         return 0;
