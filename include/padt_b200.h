@@ -51,6 +51,9 @@ const char* padt_weight_name(const PadtDims* dims, int index);
 int padt_create(const PadtDims* dims, const void* const* weights, int n_weights, const void* llm_cos, const void* llm_sin,
                 int max_pos, PadtHandle** out);
 int padt_destroy(PadtHandle* h);
+/* Replace the LLM rotary tables (same layout as in padt_create) when a request needs more positions than the current table
+ * holds: the reference evaluates cos/sin per call and has no length limit (HF:595-608).  The caller keeps the tensors alive. */
+int padt_set_rope_table(PadtHandle* h, const void* llm_cos, const void* llm_sin, int max_pos);
 
 /* V1-V6: custom_visual_forward (padt.py:48-106).  pixel_values [P,1176]; grid_thw_host [n_img*3];
  * pos_cos/pos_sin: fp32 DEVICE tables [tab_rows, head_dim/4] = cos/sin(outer(arange, inv_freq)) (HF:117-130).

@@ -41,7 +41,7 @@ class PadtGenBuffers(C.Structure):
 
 #: every symbol include/padt_b200.h declares (tests/test_capi_symbols.py checks the library exports all of them)
 EXPORTED_SYMBOLS = (
-    "padt_last_error", "padt_version", "padt_launch_count", "padt_weight_count", "padt_weight_name", "padt_create", "padt_destroy",
+    "padt_last_error", "padt_version", "padt_launch_count", "padt_weight_count", "padt_weight_name", "padt_create", "padt_destroy", "padt_set_rope_table",
     "padt_vit_plan_host", "padt_vit_forward", "padt_prototypes", "padt_prefill", "padt_decode", "padt_decode_status", "padt_set_option",
     "padt_vl_decode", "padt_op_gemm", "padt_op_rmsnorm", "padt_op_attention", "padt_op_rope_neox",
     "padt_debug_mega_plan", "padt_debug_mega_partition",
@@ -87,6 +87,7 @@ def load() -> C.CDLL:
     lib.padt_create.argtypes = [C.POINTER(PadtDims), C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                 C.POINTER(C.c_void_p)]
     lib.padt_destroy.argtypes = [C.c_void_p]
+    lib.padt_set_rope_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.padt_vit_forward.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.padt_vit_plan_host.argtypes = [C.POINTER(PadtDims), C.POINTER(C.c_int64), C.c_int] + [C.c_void_p] * 5 + [C.POINTER(C.c_int32)] * 2

@@ -136,9 +136,24 @@ def padt_small(tie: bool = False) -> PadtConfig:
     )
 
 
+def padt_vit1344() -> PadtConfig:
+    """Full-width ViT (1280 / 16 heads / 3420) cut to 2 blocks (window, full attention) over a miniature LLM: the config of the
+    1344x1344 ViT parity fixture (tests/golden/vit1344.pt, oracle/make_golden.py)."""
+    vocab = 512
+    return PadtConfig(
+        name="PaDT_vit1344",
+        vision=VisionConfig(depth=2, fullatt_block_indexes=(1,), out_hidden_size=256),
+        text=TextConfig(hidden_size=256, intermediate_size=640, num_layers=1, num_heads=2, num_kv_heads=1, vocab_size=vocab),
+        decoder=DecoderConfig(),
+        image_token_id=vocab - 12, video_token_id=vocab - 11, vision_start_token_id=vocab - 14,
+        vision_end_token_id=vocab - 13, eos_token_ids=(vocab - 10,), pad_token_id=vocab - 9,
+    )
+
+
 PRESETS = {
     "PaDT_Pro_3B": padt_pro_3b,
     "PaDT_Pro_7B": padt_pro_7b,
     "PaDT_tiny": padt_tiny,
     "PaDT_small": padt_small,
+    "PaDT_vit1344": padt_vit1344,
 }

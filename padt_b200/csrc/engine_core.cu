@@ -235,6 +235,17 @@ extern "C" int padt_create(const PadtDims* dims, const void* const* weights, int
     return 0;
 }
 
+extern "C" int padt_set_rope_table(PadtHandle* h, const void* llm_cos, const void* llm_sin, int max_pos) {
+    PADT_REQUIRE(h && llm_cos && llm_sin && max_pos > 0, "null argument");
+    cudaDeviceSynchronize();   // a decode launch in flight may still read the old table
+    h->cos_tab = reinterpret_cast<const bf16*>(llm_cos);
+    h->sin_tab = reinterpret_cast<const bf16*>(llm_sin);
+    h->max_pos = max_pos;
+    h->gen_ready = false;      // generation state (and any captured graph) refers to the old table
+    if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
+    return 0;
+}
+
 extern "C" int padt_destroy(PadtHandle* h) {
     if (!h) return 0;
     cudaDeviceSynchronize();

@@ -21,7 +21,7 @@ def _stream() -> int:
 
 
 class PadtEngine:
-    MAX_POS = 8192          # rows of the LLM rotary table (positions; prompt + generation must stay below)
+    MAX_POS = 8192          # initial rows of the LLM rotary table; grown on demand (the reference has no length limit)
     MAX_GRID = 1024         # rows of the ViT rotary table (patches per image side)
 
     def __init__(self, cfg: PadtConfig, weights: Dict[str, torch.Tensor]):
@@ -48,13 +48,8 @@ class PadtEngine:
             ptrs[i] = w.data_ptr()
             self._keep.append(w)
         self.device = self._keep[0].device
-        # LLM rotary tables, evaluated like HF:595-608 (fp32 on the host, cast to bf16)
-        t = cfg.text
-        hd = t.head_dim
-        inv_freq = 1.0 / (t.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).to(torch.float) / hd))
-        freqs = torch.outer(torch.arange(self.MAX_POS, dtype=torch.float32), inv_freq.float())
-        self.llm_cos = freqs.cos().to(torch.bfloat16).to(self.device).contiguous()
-        self.llm_sin = freqs.sin().to(torch.bfloat16).to(self.device).contiguous()
+        self.max_pos = self.MAX_POS
+        self.llm_cos, self.llm_sin = self._llm_rope_table(self.max_pos)
         # ViT rotary tables (HF:117-130 with dim = head_dim/2)
         vd = cfg.vision.head_dim // 2
         vinv = 1.0 / (10000.0 ** (torch.arange(0, vd, 2, dtype=torch.float) / vd))
@@ -67,6 +62,23 @@ class PadtEngine:
                                              C.byref(handle)), "padt_create")
         self.handle = handle
         self._gen_keep = None
+
+    def _llm_rope_table(self, n_pos: int):
+        """LLM rotary tables, evaluated like HF:595-608 (fp32 on the host, cast to bf16)."""
+        t = self.cfg.text
+        hd = t.head_dim
+        inv_freq = 1.0 / (t.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).to(torch.float) / hd))
+        freqs = torch.outer(torch.arange(n_pos, dtype=torch.float32), inv_freq.float())
+        return (freqs.cos().to(torch.bfloat16).to(self.device).contiguous(), freqs.sin().to(torch.bfloat16).to(self.device).contiguous())
+
+    def _ensure_positions(self, n_pos: int):
+        if n_pos <= self.max_pos:
+            return
+        new = (n_pos + self.MAX_POS - 1) // self.MAX_POS * self.MAX_POS
+        cos, sin = self._llm_rope_table(new)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.padt_set_rope_table(self.handle, cos.data_ptr(), sin.data_ptr(), new), "padt_set_rope_table")
+        self.llm_cos, self.llm_sin, self.max_pos = cos, sin, new
 
     def close(self):
         if getattr(self, "handle", None):
@@ -119,8 +131,8 @@ class PadtEngine:
         B, L = input_ids.shape
         D = self.cfg.text.hidden_size
         dev = self.device
-        if L + max_steps + 1 > self.MAX_POS:
-            raise ValueError(f"prompt ({L}) + max_new_tokens ({max_steps}) exceeds the rotary table ({self.MAX_POS})")
+        # positions never exceed the padded length + generated tokens (rope_delta <= 0, padt.py:266-276)
+        self._ensure_positions(L + max_steps + 1)
         bufs = dict(
             tokens=torch.zeros((max_steps, B), dtype=torch.int64, device=dev),
             argmax=torch.zeros((max_steps, B), dtype=torch.int64, device=dev),

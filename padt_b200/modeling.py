@@ -129,7 +129,15 @@ class PaDTForConditionalGeneration:
                  image_grid_thw: torch.Tensor = None, use_cache: bool = True, max_new_tokens: int = 20, do_sample: bool = False,
                  output_hidden_states: bool = False, return_dict_in_generate: bool = False, synced_gpus: bool = False,
                  eos_token_id=None, pad_token_id=None, forced_tokens: Optional[torch.Tensor] = None, prototype_group=None,
-                 _prefill_only: bool = False, **unused):
+                 global_image_grid_thw: Optional[torch.Tensor] = None, _prefill_only: bool = False, **unused):
+        """``prototype_group`` (a torch.distributed group) switches on the sample-sharded mode: this rank's
+        rows are generated exactly as in a single-process run of the LOCAL batch -- ``sequences``, ``past_image_embeds``,
+        ``past_logit_mask`` are rank-local, so the reference flow ``assign_to_local_vrt_id(seq, local_grid)`` ->
+        ``parseVRTintoCompletion`` -> ``vl_decode(feats, out.past_image_embeds, ..., local_grid, ...)`` is correct on every
+        rank -- while ONE all-gather of the prototype rows runs on a side stream.  ``out.global_view()`` waits for it and
+        returns the single-process view of the whole batch: (global table, row offset of this rank, sequences with
+        VRT ids shifted by that offset).  ``global_image_grid_thw`` [B_global,3] (rank-strided samples) lets the row counts be
+        derived from the grids, without a count collective."""
         cfg = self.padt_config
         if do_sample:
             raise NotImplementedError("only greedy decoding (do_sample=False), the mode every reference script uses (utils.py:233-236)")
@@ -152,12 +160,17 @@ class PaDTForConditionalGeneration:
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + int(c))
+        exchange = None
         if prototype_group is not None:
-            # sample-sharded inference: ONE all-gather of past_image_embeds so that every rank holds the
-            # batch-global VRT table / id space of the single-process reference (padt_processor.py:36-42)
-            from .distributed import allgather_prototypes
-            protos, base = allgather_prototypes(protos, prototype_group)
-            offs = [o + base for o in offs]
+            # sample-sharded inference: ONE all-gather of past_image_embeds, on a side stream -- decode reads only
+            # the local rows, so the collective overlaps the local prefill + decode instead of sitting between ViT and prefill
+            import torch.distributed as dist
+            from .distributed import PrototypeExchange, rank_row_counts
+            rc = None
+            if global_image_grid_thw is not None:
+                rc = rank_row_counts(global_image_grid_thw.detach().to("cpu", torch.int64), dist.get_world_size(prototype_group),
+                                     cfg.vision.spatial_merge_size)
+            exchange = PrototypeExchange(protos, prototype_group, rc)
         n_table = protos.shape[0]
         V = cfg.text.vocab_size
         if int(ids_cpu.max()) >= V + n_table:
@@ -225,6 +238,11 @@ class PaDTForConditionalGeneration:
             past_image_embeds=protos, past_logit_mask=logit_mask, past_high_res_image_embeds=high_res, past_visual_pe=visual_pe,
             argmax_tokens=bufs["argmax"][:t_gen].t(),
         )
+        if exchange is not None:
+            def global_view(_ex=exchange, _seq=sequences, _V=V):
+                table, base = _ex.wait()
+                return table, base, torch.where(_seq >= _V, _seq + base, _seq)
+            out["global_view"] = global_view
         return out if return_dict_in_generate else sequences
 
     # ------------------------------------------------------------------ vl_decode (padt.py:342-412)

@@ -7,6 +7,9 @@ Key layout follows SURVEY.md §5 / Appendix A: ``visual.*``, ``model.layers.*``,
 There is no checkpoint offline, so benchmarks/tests use ``random_weights``: N(0, 0.02) matrices, small random
 biases, norm weights near 1, and ``vis_norm.weight ~ 0.02`` so prototype rows sit on the scale of text rows
 (the reference zero-inits it, padt.py:134-139, which makes every VRT logit exactly 0).
+The PaDT decoder (``vl_decoder.*``) gets variance-preserving matrices N(0, 1/fan_in) and N(0, 0.1) biases: with
+N(0, 0.02) its heads collapse to sigmoid(~0) = 0.5 boxes and ~1e-2 mask logits, which no parity test can tell from
+a constant; with this init boxes span ~0.05..0.95, scores are O(1) and mask logits O(1) (std ~1.3, |max| ~6).
 """
 from __future__ import annotations
 
@@ -147,9 +150,11 @@ def random_weights(cfg: PadtConfig, seed: int = 0, device="cpu", dtype=torch.bfl
         elif _is_norm(name):
             w = 1.0 + 0.05 * r
         elif name.endswith(".bias"):
-            w = std * r
+            w = (0.1 if name.startswith("vl_decoder.") else std) * r
         elif name in ("vl_decoder.vp_embedding.weight", "vl_decoder.bbox_score_mask_tokens.weight"):
             w = r  # nn.Embedding default init N(0,1)
+        elif name.startswith("vl_decoder.") and len(shp) == 2:
+            w = r / float(shp[1]) ** 0.5
         else:
             w = std * r
         out[name] = w.to(dtype)

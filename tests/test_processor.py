@@ -126,3 +126,36 @@ def test_processor_wrapper_growth_and_passthrough():
         assert False
     except AttributeError:
         pass
+
+
+def test_parser_against_reference_cross_run():
+    """tests/golden/parser_cases.json: 200 random piece streams that oracle/make_golden.py ran through the UNMODIFIED reference
+    parser and processor wrapper (padt_processor.py:4-151); this module must reproduce every output (completions, labels, VRT strings,
+    which hidden-state steps were gathered, which prototype rows were looked up, the global id shift)."""
+    import json
+    import os
+    from helpers import ROOT
+    with open(os.path.join(ROOT, "tests", "golden", "parser_cases.json")) as f:
+        data = json.load(f)
+    strings = {i: a for i, a in enumerate(data["alphabet"])}
+    n_obj = 0
+    for ci, c in enumerate(data["cases"]):
+        V = c["V"]
+        ids = torch.tensor(c["ids"])
+        grid = torch.tensor(c["grids"])
+        B, T = ids.shape
+        Ms = [g[1] * g[2] // 4 for g in c["grids"]]
+        proc = VisonTextProcessingClass(FakeProcessor(V, strings))
+        proc.model_embed_token_size = V
+        hidden = [(torch.arange(B, dtype=torch.float32).view(B, 1, 1) * 1000 + float(s),) for s in range(T)]
+        protos = torch.arange(sum(Ms), dtype=torch.float32)[:, None]
+        comp, feats, labels, vrts, vf = parseVRTintoCompletion(proc, ids.clone(), hidden, torch.tensor(c["thinking"]), protos, grid)
+        e = c["expect"]
+        assert comp == e["completions"] and labels == e["labels"] and vrts == e["vrts"], ci
+        assert [[f.flatten().tolist() for f in fs] for fs in feats] == e["feat_steps"], ci
+        assert [[f.flatten().tolist() for f in fs] for fs in vf] == e["proto_rows"], ci
+        x = ids.clone()
+        assert proc.assign_to_global_vrt_id(x, grid).tolist() == e["global_ids"], ci
+        assert torch.equal(proc.assign_to_local_vrt_id(x, grid), ids), ci
+        n_obj += sum(len(l) for l in labels)
+    assert len(data["cases"]) >= 200 and n_obj > 100
