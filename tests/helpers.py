@@ -50,7 +50,7 @@ def report(what: str, **kv):
     print("[parity]", what, kv)
 
 
-def assert_box_like(a, b, what, ulps: float = 2.0, abs_tol: float = 1e-3):
+def assert_box_like(a, b, what, ulps: float = 2.0, abs_tol: float = 1e-3, check: bool = True):
     """North-star float bar for boxes / scores / mask logits: |cand - ref| <= 1e-3, or <= `ulps` bf16 ulps of the reference
     value where bf16 itself is coarser than 1e-3 (the reference emits bf16: spacing at 0.5 is 3.9e-3, at 4.0 3.1e-2).
     Returns the report dict (max abs diff, how many elements exceed 1e-3, how many needed the ulp clause)."""
@@ -62,7 +62,8 @@ def assert_box_like(a, b, what, ulps: float = 2.0, abs_tol: float = 1e-3):
     rep = dict(n=int(d.numel()), max_abs=float(d.max()), n_gt_1e3=int((d > abs_tol).sum()), n_bad=int(bad.sum()),
                ref_min=float(b32.min()), ref_max=float(b32.max()), worst_ulps=float((d / ulp).max()))
     report(what, **rep)
-    assert not bool(bad.any()), f"{what}: {rep}"
+    if check:
+        assert not bool(bad.any()), f"{what}: {rep}"
     return rep
 
 
