@@ -31,8 +31,6 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     size_t o_av = take((size_t)p.n_amax_blocks * B * 4), o_ai = take((size_t)p.n_amax_blocks * B * 4);
     size_t o_cnt = take((size_t)B * d.n_kv_heads * 4 * 2), o_tok = take((size_t)B * 8);
     size_t o_xp = take((size_t)(h->n_sms + 1) * 64 * 8);   // [B*nkv] re-armed counters (decode.cu) + [B*nkv] monotonic (decode_mega.cu)
-    const size_t ll_words = decode_mega_ll_alloc_words(p);   // needs p.B / p.n_split (set above)
-    size_t o_ll = take(ll_words * 8);
     bool fresh = off > h->dec_ws.bytes;
     RC(h->dec_ws.ensure(off));
     uint8_t* b = h->dec_ws.as<uint8_t>();
@@ -42,8 +40,6 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     p.attn_counters = (int*)(b + o_cnt); p.cur_token = (long long*)(b + o_tok);
     p.xpart = (unsigned long long*)(b + o_xp);
     PADT_CHECK_CUDA(cudaMemset(p.xpart, 0, (size_t)(h->n_sms + 1) * 64 * 8));   // epoch 0 = nothing published
-    p.ll = (unsigned long long*)(b + o_ll); p.ll_words = ll_words;
-    PADT_CHECK_CUDA(cudaMemset(p.ll, 0, ll_words * 8));          // epochs restart with every generation: stale words must not match
     (void)fresh;
     PADT_CHECK_CUDA(cudaMemset(p.attn_counters, 0, (size_t)B * d.n_kv_heads * 4 * 2));
     const size_t layer_kv = (size_t)B * d.n_kv_heads * h->s_max * h->hd;

@@ -81,7 +81,6 @@ struct DecodeParams {
     bf16 *h, *qkv, *act;          // [B,D], [B,(nh+2nkv)hd], [B,max(I, nh*hd)]
     float *part_o, *part_ml; int* attn_counters; int n_split;
     unsigned long long* xpart;           // persistent kernel, balanced partition: [n_sms + 1][8][8] words {epoch, fp32 partial} of shared row groups
-    unsigned long long* ll; size_t ll_words;   // persistent kernel: LL exchange buffers {epoch, payload} (two parity copies), zeroed at prefill
     float *amax_val; int *amax_idx; int n_amax_blocks;
     bf16 *last_hidden;            // [B,D] final-norm hidden of the latest forward
     bf16 *hidden_steps;           // optional [max_steps,B,D]; entry k is the state that predicted token k
@@ -104,7 +103,6 @@ bool decode_mega_can_run(const DecodeParams& p, int n_sms);
 int decode_mega_nseg(int K);
 size_t decode_mega_image_elems(int n_rows, int K);
 int launch_pack_stage_image(const bf16* W, int n_rows, int K, bf16* out, cudaStream_t st);
-size_t decode_mega_ll_alloc_words(const DecodeParams& p);   // uint64 words of the LL exchange buffer (both parity copies, all replicas)
 int decode_mega_build_table(const DecodeParams& p, const DecodeLayerW* layers_host, int G, bool split, std::vector<uint64_t>& tab, std::vector<int>& off);
 void decode_mega_stage_range(int n_rows, int K, int G, bool balanced, int c, int* nseg, unsigned int* lo, unsigned int* hi);
 bool decode_mega_split();   // balanced (stage-granular) partition enabled (PADT_MEGA_FLAGS bit 128 / default)

@@ -1,8 +1,7 @@
 """CPU: host-side planning of the persistent decode kernel (csrc/decode_mega.cu) through the C ABI -- no device work.
 
-* shared-memory plan: fits 227 KB, the ring has >= 4 slots of ONE size that holds the largest stage of the model (every consumer
-  warp reads every stage since round 2, so the slot count no longer has to be even), the raw residual rows sit behind the
-  widest activation rows;
+* shared-memory plan: fits 227 KB, ring has an EVEN number of slots (an odd ring broke PaDT_Pro_7B: the two half-CTAs take
+  alternate stages and only wait on their own stages' barriers), one slot holds the largest stage of the model;
 * stage partition: the 148 per-CTA stage ranges tile [0, groups * nseg) exactly once, group-aligned without the balanced mode,
   sizes within one stage of each other with it, and every balanced range holds at least one whole group's worth of stages
   (so a row group is shared by at most two CTAs -- the head/tail combine in the epilogue relies on it)."""
@@ -47,19 +46,19 @@ def test_shared_memory_plan(lib, name, B):
     m = MODELS[name]
     rc, (slot_bytes, n_slots, x_bytes, smem) = _plan(lib, m, B)
     if (name, B) == ("PaDT_Pro_7B", 4):
-        # 4 rows x 18952 bf16 of down_proj activations (152 KB) + 4 raw residual rows: either a small ring still fits or the plan says no
-        # (the engine then runs the per-layer kernels of decode.cu for this batch size) -- never a ring below 4 slots
-        if rc != 0:
-            return
+        # 4 rows x 18952 bf16 of down_proj activations (152 KB) leave no room for a 4-slot ring: the engine then runs the
+        # per-layer kernels (decode.cu) for this batch size -- the plan must say so instead of producing a tiny ring
+        assert rc != 0
+        return
     assert rc == 0
-    assert n_slots >= 4
+    assert n_slots % 2 == 0 and n_slots >= 4, "the ring must have an even number of slots"
     assert smem <= 227 * 1024 - 4 * 1024, "dynamic + ~3.5 KB static shared memory must fit one SM"
     assert slot_bytes % 128 == 0
     for K in (m["D"], m["nh"] * 128, m["I"]):
         nseg, stage_bytes = _nseg_and_stage_bytes(lib, K)
         assert K % (16 * nseg) == 0 and stage_bytes <= slot_bytes
     kmax = max(m["D"], m["I"])
-    assert x_bytes >= B * (kmax + 8) * 2 + 2 * B * m["D"] * 2, "activation rows of the widest phase + two raw residual rows"
+    assert x_bytes >= B * (kmax + 8) * 2, "activation rows of the widest phase"
     assert x_bytes >= B * (m["D"] + 8) * 2 + 2 * 64 * 136 * 2, "K/V tiles sit behind the q/k/v activation rows"
 
 
