@@ -33,114 +33,7 @@ from padt_b200.weights import random_weights  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def _eager_fa2(module, query, key, value, attention_mask, scaling, dropout=0.0, **kwargs):
-    """Replacement for HF `eager_attention_forward` (HF:182-204) with FA2 numerics."""
-    B = query.shape[0]
-    outs = []
-    for b in range(B):
-        mask = None
-        if attention_mask is not None:
-            mask = attention_mask[b, 0] > -1.0
-        outs.append(O.fa2_attention(query[b], key[b], value[b], scaling, mask))
-    out = torch.stack(outs, 0).transpose(1, 2).contiguous()
-    return out, None
-
-
-def build_reference(cfg, weights):
-    padt, dec, proc = ref_shim.install()
-    import transformers.models.qwen2_5_vl.modeling_qwen2_5_vl as hf
-    from transformers import Qwen2_5_VLConfig
-    hf.eager_attention_forward = _eager_fa2
-    t, v, d = cfg.text, cfg.vision, cfg.decoder
-    hc = Qwen2_5_VLConfig(
-        text_config=dict(vocab_size=t.vocab_size, hidden_size=t.hidden_size, intermediate_size=t.intermediate_size,
-                         num_hidden_layers=t.num_layers, num_attention_heads=t.num_heads,
-                         num_key_value_heads=t.num_kv_heads, rms_norm_eps=t.rms_norm_eps,
-                         rope_parameters=dict(rope_type="default", rope_theta=t.rope_theta,
-                                              mrope_section=list(t.mrope_section)),
-                         tie_word_embeddings=t.tie_word_embeddings, use_sliding_window=False,
-                         max_position_embeddings=4096, pad_token_id=None),
-        vision_config=dict(depth=v.depth, hidden_size=v.hidden_size, intermediate_size=v.intermediate_size,
-                           num_heads=v.num_heads, out_hidden_size=v.out_hidden_size,
-                           fullatt_block_indexes=list(v.fullatt_block_indexes), window_size=v.window_size,
-                           patch_size=v.patch_size, spatial_merge_size=v.spatial_merge_size,
-                           temporal_patch_size=v.temporal_patch_size),
-        image_token_id=cfg.image_token_id, video_token_id=cfg.video_token_id,
-        vision_start_token_id=cfg.vision_start_token_id, vision_end_token_id=cfg.vision_end_token_id,
-        tie_word_embeddings=t.tie_word_embeddings,
-    )
-    hc.hidden_size = t.hidden_size
-    hc.vocab_size = t.vocab_size
-    hc.vl_decoder = dict(name="PaDTDecoder", attn_implementation="flash_attention_2", hidden_size=d.hidden_size,
-                         intermediate_size=d.intermediate_size, llm_hidden_state=t.hidden_size,
-                         num_heads=d.num_heads, spatial_merge_size=v.spatial_merge_size, use_mask_loss=True)
-    hc.use_visual_prototype_projection = cfg.use_visual_prototype_projection
-    hc._attn_implementation = "eager"
-    hc.text_config._attn_implementation = "eager"
-    hc.vision_config._attn_implementation = "eager"
-    # like from_pretrained(torch_dtype=bf16): instantiate under a bf16 default dtype so parameters are bf16 while
-    # the explicitly-fp32 rotary inv_freq buffers stay fp32 (a later .to(bf16) would round them)
-    torch.set_default_dtype(torch.bfloat16)
-    try:
-        model = padt.PaDTForConditionalGeneration(hc).eval()
-    finally:
-        torch.set_default_dtype(torch.float32)
-    model.vl_decoder.dtype = torch.bfloat16
-    assert model.model.visual.rotary_pos_emb.inv_freq.dtype == torch.float32
-    assert model.model.language_model.rotary_emb.inv_freq.dtype == torch.float32
-    # 4.50 attribute layout expected by padt.py (SURVEY.md §8c step 4)
-    model.__dict__["visual"] = model.model.visual
-    model.model.embed_tokens = model.model.language_model.embed_tokens
-    model.rope_deltas = None
-    model.get_rope_index = lambda input_ids=None, image_grid_thw=None, video_grid_thw=None, second_per_grid_ts=None, attention_mask=None: \
-        O.get_rope_index(cfg, input_ids, image_grid_thw, attention_mask)
-    sd = {}
-    for k, val in weights.items():
-        if k.startswith("visual."):
-            nk = "model." + k
-        elif k.startswith("model."):
-            nk = "model.language_model." + k[len("model."):]
-        else:
-            nk = k
-        sd[nk] = val
-    missing, unexpected = model.load_state_dict(sd, strict=False)
-    missing = [m for m in missing if "inv_freq" not in m and m != "model.embed_tokens.weight"  # alias of language_model.embed_tokens
-               and not (t.tie_word_embeddings and m == "lm_head.weight")]
-    assert not missing and not unexpected, (missing, unexpected)
-    if t.tie_word_embeddings:
-        model.lm_head.weight = model.model.language_model.embed_tokens.weight
-    return model, proc
-
-
-def ref_greedy(model, cfg, input_ids, attention_mask, pixel_values, grid, steps, forced=None):
-    """padt.py:671-757 restated around the reference's own forward_main (eos disabled -> fixed length)."""
-    from transformers import DynamicCache
-    B, L = input_ids.shape
-    cache = DynamicCache(config=model.config)
-    model.rope_deltas = None
-    out = model.forward_main(input_ids=input_ids, attention_mask=attention_mask, pixel_values=pixel_values,
-                             image_grid_thw=grid, past_key_values=cache, use_cache=True, output_hidden_states=True,
-                             return_dict=True, cache_position=torch.arange(L))
-    past = dict(past_image_embeds=out.past_image_embeds, past_logit_mask=out.past_logit_mask,
-                past_high_res_image_embeds=out.past_high_res_image_embeds, past_visual_pe=out.past_visual_pe)
-    seq, mask = input_ids.clone(), attention_mask.clone()
-    hid, logit_steps, arg_steps = [out.hidden_states[-1]], [], []
-    for s in range(steps):
-        scores = out.logits[:, -1, :].clone().float()
-        logit_steps.append(scores)
-        nxt = torch.argmax(scores, dim=-1)
-        arg_steps.append(nxt.clone())
-        if forced is not None:
-            nxt = forced[:, s].clone()
-        seq = torch.cat([seq, nxt[:, None]], dim=-1)
-        if s == steps - 1:
-            break
-        mask = torch.cat([mask, torch.ones(B, 1, dtype=mask.dtype)], dim=-1)
-        out = model.forward_main(input_ids=nxt[:, None], attention_mask=mask, past_key_values=cache, use_cache=True,
-                                 output_hidden_states=True, return_dict=True,
-                                 cache_position=torch.tensor([L + s]), **past)
-        hid.append(out.hidden_states[-1])
-    return dict(sequences=seq, hidden_steps=hid, logits_steps=logit_steps, argmax_steps=arg_steps, **past)
+from ref_runner import build_reference, ref_greedy  # noqa: E402,F401  (shared with bench.py and the GPU floor test)
 
 
 def make_inputs(cfg, grids, prompt_lens, seed, pre_len=3, text_hi=None):

@@ -19,7 +19,23 @@ import math
 import torch
 import torch.nn.functional as F
 
-REF_SRC = "/root/reference/src"
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ref_src():
+    """/root/reference/src in the build container; the staged byte-for-byte copy under oracle/_ref/ elsewhere (oracle/stage_ref.py)."""
+    if os.path.isdir("/root/reference/src/PaDT/models"):
+        return "/root/reference/src"
+    staged = os.path.join(_HERE, "_ref")
+    if os.path.exists(os.path.join(staged, "PaDT", "models", "padt.py")):
+        return staged
+    raise FileNotFoundError("the reference model files are neither under /root/reference nor staged under oracle/_ref "
+                            "(run `python oracle/stage_ref.py` in the build container)")
+
+
+REF_SRC = None   # resolved by install()
 
 
 def _apply_rotary_emb(x, cos, sin):
@@ -57,12 +73,21 @@ def _flash_attn_varlen_func(q, k, v, cu_q, cu_k, max_q, max_k, causal=False, sof
     return out
 
 
-def install():
+def install(use_flash_attn: bool = False):
+    """use_flash_attn=True (GPU baseline): the three names padt_decoder.py:8 imports are the REAL flash-attn functions
+    (flash_attn.flash_attn_varlen_func, flash_attn.layers.rotary.apply_rotary_emb), as in the reference's own environment."""
+    global REF_SRC
+    REF_SRC = _ref_src()
     if "deepspeed" not in sys.modules:
         sys.modules["deepspeed"] = types.ModuleType("deepspeed")
     import transformers.models.qwen2_5_vl.modeling_qwen2_5_vl as hf
-    if not hasattr(hf, "Qwen2RMSNorm"):
-        hf.Qwen2RMSNorm = hf.Qwen2_5_VLRMSNorm
+    hf.Qwen2RMSNorm = hf.Qwen2_5_VLRMSNorm
+    if use_flash_attn:
+        from flash_attn import flash_attn_varlen_func
+        from flash_attn.layers.rotary import apply_rotary_emb
+        hf.apply_rotary_emb = apply_rotary_emb
+        hf.flash_attn_varlen_func = flash_attn_varlen_func
+    else:
         hf.apply_rotary_emb = _apply_rotary_emb
         hf.flash_attn_varlen_func = _flash_attn_varlen_func
     if REF_SRC not in sys.path:
@@ -78,4 +103,7 @@ def install():
     padt = importlib.import_module("PaDT.models.padt")
     dec = importlib.import_module("PaDT.models.padt_decoder")
     proc = importlib.import_module("PaDT.models.padt_processor")
+    # padt_decoder.py:8 binds the three names at import time: rebind them in case the module was imported under the other mode
+    dec.apply_rotary_emb = hf.apply_rotary_emb
+    dec.flash_attn_varlen_func = hf.flash_attn_varlen_func
     return padt, dec, proc
