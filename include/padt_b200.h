@@ -79,8 +79,13 @@ typedef struct PadtGenBuffers {
     void* hidden_steps;     /* [max_steps,B,D] final-norm state that predicted token k (padt.py:732-737), may be NULL */
     void* last_hidden;      /* [B,D] */
     void* prefill_hidden;   /* [B,L,D] final-norm states of the prompt (hidden_states[0][-1]), may be NULL */
-    const int64_t* forced;  /* [max_steps,B] teacher-forced feedback tokens, may be NULL */
+    const int64_t* forced;  /* [max_steps,B] teacher-forced feedback tokens, may be NULL.  The sampler reads entry t when it samples token t,
+                             * so a caller that picks tokens itself (do_sample / logits processors, padt.py:717,740-745) writes entry t on the
+                             * stream before the decode call that samples it. */
     int32_t max_steps;
+    void* logits_out;       /* [B, logits_ld] bf16: the masked, bf16-rounded extended logits of the latest forward (padt.py:292-301,713), may be
+                             * NULL.  Columns no row may emit are not computed: the caller pre-fills the buffer with -inf. */
+    int32_t logits_ld;
 } PadtGenBuffers;
 
 /* E2-E4, R1, T1, T2 (prefill): forward_main pixel_values branch after the ViT (padt.py:193-219,256-301).
@@ -119,6 +124,10 @@ int padt_op_attention(const void* q, const void* k, const void* v, void* o, int6
                       int64_t v_row, int64_t v_head, int64_t o_row, int64_t o_head, const int32_t* q_off, const int32_t* q_len,
                       const int32_t* k_off, const int32_t* k_len, const int32_t* k_start, int n_seg, int n_heads, int group,
                       int max_q_len, int head_dim, int causal, float scale, padt_stream_t stream);
+/* padt.py:301: logits.masked_fill_(~logit_mask[:, None, :], -inf) for the teacher-forced forward: logits [B*rows_per_sample, ld] bf16, columns
+ * >= vocab outside [vocab + vrt_lo[b], vocab + vrt_hi[b]) of sample b become -inf.  B <= 16. */
+int padt_op_logit_mask(void* logits, int64_t ld, int rows_per_sample, int B, int vocab, int n_ext, const int32_t* vrt_lo_host,
+                       const int32_t* vrt_hi_host, padt_stream_t stream);
 int padt_op_rope_neox(void* x, int64_t row_stride, int n_heads, int head_dim, const float* cos, const float* sin, int cs_ld, int rows,
                       padt_stream_t stream);
 

@@ -34,6 +34,7 @@ struct GemvArgs {
     bf16* last_hidden;    // PRO_RMSNORM + GE_LOGITS: normalised rows also stored here
     bf16* hidden_steps;   // optional log [T,B,K]
     int max_steps;
+    bf16* logits_out; int logits_ld;   // optional [B, logits_ld] masked bf16 logits (sampling / logits processors)
 };
 
 template <int NB, int PRO, int EPI>
@@ -117,6 +118,10 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_kernel(GemvArgs a) {
                 bool ok1 = has1 && (n1 < a.vocab || (n1 - a.vocab >= vlo[b] && n1 - a.vocab < vhi[b]));
                 if (ok0 && (l0 > best_v[b] || (l0 == best_v[b] && n0 < best_i[b]))) { best_v[b] = l0; best_i[b] = n0; }
                 if (ok1 && (l1 > best_v[b] || (l1 == best_v[b] && n1 < best_i[b]))) { best_v[b] = l1; best_i[b] = n1; }
+                if (a.logits_out && lane == 0 && b < a.B) {
+                    a.logits_out[(size_t)b * a.logits_ld + n0] = f2bf(ok0 ? l0 : -INFINITY);
+                    if (has1) a.logits_out[(size_t)b * a.logits_ld + n1] = f2bf(ok1 ? l1 : -INFINITY);
+                }
             }
         } else if (lane == 0) {
 #pragma unroll
@@ -222,6 +227,7 @@ int launch_final_logits(const DecodeParams& p, cudaStream_t st) {
     a.W = p.head; a.W2 = p.protos; a.B = p.B; a.N = p.vocab + p.n_protos; a.K = p.D; a.vocab = p.vocab;
     a.state = p.dev_state; a.amax_val = p.amax_val; a.amax_idx = p.amax_idx;
     a.last_hidden = p.last_hidden; a.hidden_steps = p.hidden_steps; a.max_steps = p.max_steps;
+    a.logits_out = p.logits_out; a.logits_ld = p.logits_ld;
     PADT_REQUIRE(p.n_amax_blocks >= gemv_grid(a.N), "arg-max partial buffer too small");
     return launch_gemv<PRO_RMSNORM, GE_LOGITS>(a, gemv_grid(a.N), st);
 }

@@ -544,6 +544,7 @@ __device__ __forceinline__ void consume_seg(const MegaArgs& a, const Seg& s, int
                         bool ok = n < p.vocab || (n - p.vocab >= am.lo[pass][lane] && n - p.vocab < am.hi[pass][lane]);
                         const float bv = am.v[pass][lane];
                         if (ok && (l0 > bv || (l0 == bv && n < am.i[pass][lane]))) { am.v[pass][lane] = l0; am.i[pass][lane] = n; }
+                        if (p.logits_out) p.logits_out[(size_t)eb * p.logits_ld + n] = f2bf(ok ? l0 : -INFINITY);
                     }
                 }
             }

@@ -264,6 +264,24 @@ int launch_add_bcast_row(const bf16* a, const bf16* row, bf16* y, int rows, int 
     PADT_LAUNCH_CHECK();
     return 0;
 }
+namespace {
+__global__ void logit_mask_kernel(bf16* __restrict__ logits, long long ld, int rows_per_sample, int vocab, int n_extra, LogitMaskRanges r, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one (row, VRT column) per thread
+    if (i >= total) return;
+    const long long row = i / n_extra;
+    const int c = (int)(i % n_extra);
+    const int b = (int)(row / rows_per_sample);
+    if (c < r.lo[b] || c >= r.hi[b]) logits[row * ld + vocab + c] = __float2bfloat16_rn(-INFINITY);
+}
+}  // namespace
+int launch_logit_mask(bf16* logits, long long ld, int rows_per_sample, int B, int vocab, int n_ext, const LogitMaskRanges& r, cudaStream_t st) {
+    const int n_extra = n_ext - vocab;
+    const long long total = (long long)B * rows_per_sample * n_extra;
+    if (total <= 0) return 0;
+    logit_mask_kernel<<<nblk(total, 256), 256, 0, st>>>(logits, ld, rows_per_sample, vocab, n_extra, r, total);
+    PADT_LAUNCH_CHECK();
+    return 0;
+}
 int launch_sigmoid(bf16* x, long long n, cudaStream_t st) {
     if (n == 0) return 0;
     sigmoid_kernel<<<nblk(n, 256), 256, 0, st>>>(x, n);

@@ -50,6 +50,7 @@ int setup_decode_params(PadtHandle* h, int B, int L, int n_protos, const void* p
     p.last_hidden = (bf16*)h->gen.last_hidden; p.hidden_steps = (bf16*)h->gen.hidden_steps;
     p.tokens_out = (long long*)h->gen.tokens_out; p.argmax_out = (long long*)h->gen.argmax_out;
     p.forced = (const long long*)h->gen.forced; p.max_steps = h->gen.max_steps;
+    p.logits_out = (bf16*)h->gen.logits_out; p.logits_ld = h->gen.logits_ld;
     return 0;
 }
 
@@ -89,6 +90,7 @@ extern "C" int padt_prefill(PadtHandle* h, const int64_t* input_ids, const int32
     PADT_REQUIRE(B >= 1 && B <= 8 && L >= 1, "batch must be 1..8 rows per GPU");
     PADT_REQUIRE(bufs->tokens_out && bufs->last_hidden && bufs->max_steps >= 1, "generation buffers");
     PADT_REQUIRE(prototypes != nullptr || n_protos == 0, "prototypes");
+    PADT_REQUIRE(bufs->logits_out == nullptr || bufs->logits_ld >= h->d.vocab + n_protos, "logits_out row length");
     cudaStream_t st = (cudaStream_t)stream;
     const PadtDims& d = h->d;
     const int D = d.D, I = d.I, nh = d.n_heads, nkv = d.n_kv_heads, hd = h->hd;

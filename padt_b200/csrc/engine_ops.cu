@@ -29,6 +29,17 @@ extern "C" int padt_op_rope_neox(void* x, int64_t row_stride, int n_heads, int h
 }
 
 // ---- host-only planning helpers of the persistent decode kernel (no device work; used by the CPU tests)
+extern "C" int padt_op_logit_mask(void* logits, int64_t ld, int rows_per_sample, int B, int vocab, int n_ext, const int32_t* vrt_lo_host,
+                                  const int32_t* vrt_hi_host, padt_stream_t stream) {
+    PADT_REQUIRE(logits && vrt_lo_host && vrt_hi_host && B >= 1 && B <= 16 && rows_per_sample >= 1 && n_ext >= vocab && ld >= n_ext, "arguments");
+    LogitMaskRanges r = {};
+    for (int b = 0; b < B; ++b) {
+        PADT_REQUIRE(vrt_lo_host[b] >= 0 && vrt_lo_host[b] <= vrt_hi_host[b] && vrt_hi_host[b] <= n_ext - vocab, "VRT range");
+        r.lo[b] = vrt_lo_host[b]; r.hi[b] = vrt_hi_host[b];
+    }
+    return launch_logit_mask((bf16*)logits, ld, rows_per_sample, B, vocab, n_ext, r, (cudaStream_t)stream);
+}
+
 extern "C" int padt_debug_mega_plan(int D, int I, int n_heads, int n_kv_heads, int B, int32_t* out4) {
     PADT_REQUIRE(out4 && n_heads > 0 && D % n_heads == 0, "arguments");
     DecodeParams p = {};

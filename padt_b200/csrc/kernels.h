@@ -56,6 +56,8 @@ int launch_embed_gather(const long long* ids, int n_tok, const bf16* embed, int 
                         const bf16* image_embeds, const int* image_slot, int dim, bf16* out, int* err_flag, cudaStream_t st);
 
 int launch_sigmoid(bf16* x, long long n, cudaStream_t st);
+struct LogitMaskRanges { int lo[16], hi[16]; };
+int launch_logit_mask(bf16* logits, long long ld, int rows_per_sample, int B, int vocab, int n_ext, const LogitMaskRanges& r, cudaStream_t st);
 
 // ------------------------------------------------------------------ decode step (decode.cu)
 struct DecodeLayerW {
@@ -88,6 +90,7 @@ struct DecodeParams {
     long long *argmax_out;        // [max_steps,B] raw arg-max of every step (differs from tokens_out when forced / finished)
     const long long *forced;      // optional [max_steps,B] teacher-forced tokens
     int max_steps;
+    bf16 *logits_out; int logits_ld;   // optional [B, logits_ld]: masked bf16 logits of the latest forward (sampling / logits processors)
     int *dev_state;
     long long *cur_token;         // [B]
     const long long *eos_ids; int n_eos; long long pad_id;

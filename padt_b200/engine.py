@@ -37,6 +37,7 @@ class PadtEngine:
             raise _capi.PadtError(f"weight inventory mismatch: library {n} vs python {len(names)}")
         ptrs = (C.c_void_p * n)()
         self._keep: List[torch.Tensor] = []
+        self._keep_by_name: Dict[str, torch.Tensor] = {}
         for i, name in enumerate(names):
             cname = self.lib.padt_weight_name(C.byref(self.dims), i).decode()
             if cname != name:
@@ -47,6 +48,7 @@ class PadtEngine:
                 raise _capi.PadtError(f"weight {name}: expected contiguous cuda bf16 {shape}, got {tuple(w.shape)} {w.dtype} {w.device}")
             ptrs[i] = w.data_ptr()
             self._keep.append(w)
+            self._keep_by_name[name] = w
         self.device = self._keep[0].device
         self.max_pos = self.MAX_POS
         self.llm_cos, self.llm_sin = self._llm_rope_table(self.max_pos)
@@ -127,7 +129,7 @@ class PadtEngine:
     def prefill(self, input_ids: torch.Tensor, image_slot: torch.Tensor, pos3: torch.Tensor, kv_start: Sequence[int],
                 rope_delta: Sequence[int], vrt_lo: Sequence[int], vrt_hi: Sequence[int], image_embeds: torch.Tensor,
                 prototypes: torch.Tensor, max_steps: int, eos_ids: Sequence[int], pad_id: int, want_hidden: bool = True,
-                forced: Optional[torch.Tensor] = None):
+                forced: Optional[torch.Tensor] = None, want_logits: bool = False):
         B, L = input_ids.shape
         D = self.cfg.text.hidden_size
         dev = self.device
@@ -140,6 +142,9 @@ class PadtEngine:
             last_hidden=torch.zeros((B, D), dtype=torch.bfloat16, device=dev),
             prefill_hidden=torch.zeros((B, L, D), dtype=torch.bfloat16, device=dev) if want_hidden else None,
             forced=None if forced is None else forced.to(device=dev, dtype=torch.int64).contiguous(),
+            # masked bf16 logits of the latest forward (sampling / logits processors); columns no row may emit are never written: -inf
+            logits=torch.full((B, (self.cfg.text.vocab_size + prototypes.shape[0] + 7) // 8 * 8), float("-inf"), dtype=torch.bfloat16, device=dev)
+            if want_logits else None,
             ids=input_ids.to(device=dev, dtype=torch.int64).contiguous(),
             slot=image_slot.to(device=dev, dtype=torch.int32).contiguous(),
             pos3=pos3.to(device=dev, dtype=torch.int32).contiguous(),
@@ -155,6 +160,8 @@ class PadtEngine:
         gb.prefill_hidden = _ptr(bufs["prefill_hidden"])
         gb.forced = _ptr(bufs["forced"])
         gb.max_steps = max_steps
+        gb.logits_out = _ptr(bufs["logits"])
+        gb.logits_ld = 0 if bufs["logits"] is None else bufs["logits"].shape[1]
         with torch.cuda.device(dev):
             _capi.check(self.lib.padt_prefill(
                 self.handle, bufs["ids"].data_ptr(), bufs["slot"].data_ptr(), bufs["pos3"].data_ptr(),
@@ -173,6 +180,26 @@ class PadtEngine:
         with torch.cuda.device(self.device):
             _capi.check(self.lib.padt_decode_status(self.handle, C.byref(a), C.byref(b), _stream()), "padt_decode_status")
         return a.value, b.value
+
+    # ------------------------------------------------------------------ T2 for every position (teacher-forced forward, padt.py:292-301)
+    def extended_logits(self, hidden: torch.Tensor, prototypes: torch.Tensor, vrt_lo: Sequence[int], vrt_hi: Sequence[int]) -> torch.Tensor:
+        """hidden [B,L,D] final-norm states -> logits [B,L,V+sum M] bf16 = hidden @ cat(head, prototypes).T with -inf outside each row's own
+        VRT range.  Two GEMMs of the library write the two column ranges of ONE buffer (the concatenated table is never materialised)."""
+        B, L, D = hidden.shape
+        V, n_p = self.cfg.text.vocab_size, prototypes.shape[0]
+        head = self._keep_by_name["model.embed_tokens.weight" if self.cfg.text.tie_word_embeddings else "lm_head.weight"]
+        ld = (V + n_p + 7) // 8 * 8
+        out = torch.empty((B * L, ld), dtype=torch.bfloat16, device=self.device)
+        h2 = hidden.reshape(B * L, D).contiguous()
+        st = _stream()
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.padt_op_gemm(0, h2.data_ptr(), D, head.data_ptr(), D, None, None, 0, out.data_ptr(), ld, None, B * L, V, D, st), "logits (head rows)")
+            if n_p > 0:
+                _capi.check(self.lib.padt_op_gemm(0, h2.data_ptr(), D, prototypes.data_ptr(), D, None, None, 0, out.data_ptr() + 2 * V, ld, None,
+                                                  B * L, n_p, D, st), "logits (prototype rows)")
+                _capi.check(self.lib.padt_op_logit_mask(out.data_ptr(), ld, L, B, V, V + n_p, _capi.i32_array(vrt_lo), _capi.i32_array(vrt_hi), st),
+                            "logit mask")
+        return out.view(B, L, ld)[:, :, : V + n_p]
 
     # ------------------------------------------------------------------ D1-D4
     def vl_decode(self, vrt_feats: torch.Tensor, obj_vrt_count: Sequence[int], obj_sample: Sequence[int], low: torch.Tensor,

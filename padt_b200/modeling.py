@@ -19,6 +19,7 @@ from . import _capi
 from .config import PRESETS, DecoderConfig, PadtConfig, TextConfig, VisionConfig
 from .engine import PadtEngine
 from .rope_index import get_rope_index
+from .sampling import LogitsPipeline
 from .weights import random_weights, weight_shapes
 
 
@@ -62,7 +63,9 @@ class PaDTForConditionalGeneration:
         self.device = self.engine.device
         # attribute paths callers touch: model.model.embed_tokens.weight.shape[0] (eval/test_demo.py:31)
         self.model = SimpleNamespace(embed_tokens=SimpleNamespace(weight=weights["model.embed_tokens.weight"]))
-        self.generation_config = SimpleNamespace(eos_token_id=list(cfg.eos_token_ids), pad_token_id=cfg.pad_token_id)
+        # generation defaults the reference takes from generation_config.json (padt.py:436-447): overridden by from_pretrained
+        self.generation_config = SimpleNamespace(eos_token_id=list(cfg.eos_token_ids), pad_token_id=cfg.pad_token_id, do_sample=False,
+                                                 repetition_penalty=1.0, temperature=1.0, top_k=None, top_p=1.0)
         self.rope_deltas = None
 
     # ------------------------------------------------------------------ construction
@@ -110,12 +113,19 @@ class PaDTForConditionalGeneration:
         sd = {}
         for fn in sorted(glob.glob(os.path.join(path, "*.safetensors"))):
             sd.update(load_file(fn))
-        return cls.from_state_dict(cfg, sd, device=device)
+        gen = load_generation_config(path, cfg)
+        if gen.get("eos_token_id") is not None or gen.get("pad_token_id") is not None:
+            import dataclasses
+            cfg = dataclasses.replace(cfg, eos_token_ids=tuple(gen["eos_token_id"]), pad_token_id=gen["pad_token_id"])
+        model = cls.from_state_dict(cfg, sd, device=device)
+        for k, v in gen.items():
+            setattr(model.generation_config, k, v)
+        return model
 
     # ------------------------------------------------------------------ dispatch (padt.py:141-145)
     def forward(self, *args, is_main=True, **kwargs):
         if is_main:
-            raise NotImplementedError("teacher-forced forward_main is the training path (SURVEY.md §8f row 1); use generate()")
+            return self.forward_main(*args, **kwargs)
         return self.vl_decode(*args, **kwargs)
 
     __call__ = forward
@@ -123,36 +133,21 @@ class PaDTForConditionalGeneration:
     def eval(self):
         return self
 
-    # ------------------------------------------------------------------ generate (padt.py:414-616 -> 618-800)
-    @torch.no_grad()
-    def generate(self, input_ids: torch.Tensor = None, attention_mask: Optional[torch.Tensor] = None, pixel_values: torch.Tensor = None,
-                 image_grid_thw: torch.Tensor = None, use_cache: bool = True, max_new_tokens: int = 20, do_sample: bool = False,
-                 output_hidden_states: bool = False, return_dict_in_generate: bool = False, synced_gpus: bool = False,
-                 eos_token_id=None, pad_token_id=None, forced_tokens: Optional[torch.Tensor] = None, prototype_group=None,
-                 global_image_grid_thw: Optional[torch.Tensor] = None, _prefill_only: bool = False, **unused):
-        """``prototype_group`` (a torch.distributed group) switches on the sample-sharded mode (SURVEY.md §8e): this rank's
-        rows are generated exactly as in a single-process run of the LOCAL batch -- ``sequences``, ``past_image_embeds``,
-        ``past_logit_mask`` are rank-local, so the reference flow ``assign_to_local_vrt_id(seq, local_grid)`` ->
-        ``parseVRTintoCompletion`` -> ``vl_decode(feats, out.past_image_embeds, ..., local_grid, ...)`` is correct on every
-        rank -- while ONE all-gather of the prototype rows runs on a side stream.  ``out.global_view()`` waits for it and
-        returns the single-process view of the whole batch: (global table, row offset of this rank, sequences with
-        VRT ids shifted by that offset).  ``global_image_grid_thw`` [B_global,3] (rank-strided samples) lets the row counts be
-        derived from the grids, without a count collective."""
+    # ------------------------------------------------------------------ shared front end of generate / forward_main (padt.py:183-219, 256-277)
+    def _encode(self, input_ids, attention_mask, pixel_values, image_grid_thw):
+        """ViT + prototypes + the host-side integer tables of one batch: image slots of the <|image_pad|> tokens (masked_scatter order,
+        padt.py:219), left-pad counts, M-RoPE ids (4.50 get_rope_index), per-row VRT ranges (padt.py:196-201)."""
         cfg = self.padt_config
-        if do_sample:
-            raise NotImplementedError("only greedy decoding (do_sample=False), the mode every reference script uses (utils.py:233-236)")
         if pixel_values is None or image_grid_thw is None:
-            raise ValueError("PaDT generate needs pixel_values and image_grid_thw (text-only prompts crash in the reference too, padt.py:230-232,292)")
+            raise ValueError("PaDT needs pixel_values and image_grid_thw (text-only prompts crash in the reference too, padt.py:230-232,292)")
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [B, L]")
         B, L = input_ids.shape
         if image_grid_thw.shape[0] != B:
             raise ValueError("one image per sample (padt.py:196-201, padt_sft_trainer.py:341)")
-        dev = self.device
         ids_cpu = input_ids.detach().to("cpu", torch.int64)
         mask_cpu = torch.ones_like(ids_cpu) if attention_mask is None else attention_mask.detach().to("cpu", torch.int64)
         grid_cpu = image_grid_thw.detach().to("cpu", torch.int64)
-        # ---- ViT + prototypes
         image_embeds, high_res, visual_pe = self.engine.vit_forward(pixel_values, grid_cpu)
         protos = self.engine.prototypes(image_embeds)
         merge2 = cfg.vision.spatial_merge_size ** 2
@@ -160,20 +155,8 @@ class PaDTForConditionalGeneration:
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + int(c))
-        exchange = None
-        if prototype_group is not None:
-            # sample-sharded inference: ONE all-gather of past_image_embeds, on a side stream -- decode reads only
-            # the local rows, so the collective overlaps the local prefill + decode instead of sitting between ViT and prefill
-            import torch.distributed as dist
-            from .distributed import PrototypeExchange, rank_row_counts
-            rc = None
-            if global_image_grid_thw is not None:
-                rc = rank_row_counts(global_image_grid_thw.detach().to("cpu", torch.int64), dist.get_world_size(prototype_group),
-                                     cfg.vision.spatial_merge_size)
-            exchange = PrototypeExchange(protos, prototype_group, rc)
-        n_table = protos.shape[0]
         V = cfg.text.vocab_size
-        if int(ids_cpu.max()) >= V + n_table:
+        if int(ids_cpu.max()) >= V + protos.shape[0]:
             raise AssertionError("input_ids.max() must be below the extended vocabulary (padt.py:203)")
         is_img = ids_cpu == cfg.image_token_id
         n_tok = int(is_img.sum())
@@ -188,30 +171,110 @@ class PaDTForConditionalGeneration:
             if int(mask_cpu[b, int(kv_start[b]):].min()) != 1:
                 raise ValueError("attention_mask must be left-padded")
         pos3, deltas = get_rope_index(ids_cpu, grid_cpu, mask_cpu, cfg.image_token_id, cfg.vision_start_token_id, cfg.vision.spatial_merge_size)
-        self.rope_deltas = deltas.to(dev)
-        eos = list(cfg.eos_token_ids) if eos_token_id is None else ([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id))
-        pad = cfg.pad_token_id if pad_token_id is None else pad_token_id
+        self.rope_deltas = deltas.to(self.device)
+        return SimpleNamespace(B=B, L=L, image_embeds=image_embeds, high_res=high_res, visual_pe=visual_pe, protos=protos, offs=offs, slot=slot,
+                               kv_start=kv_start, pos3=pos3, deltas=deltas, grid_cpu=grid_cpu)
+
+    def _logit_mask(self, B, offs, n_table):
+        V = self.padt_config.text.vocab_size
+        logit_mask = torch.zeros((B, V + n_table), dtype=torch.bool, device=self.device)   # padt.py:196-201
+        logit_mask[:, :V] = True
+        for b in range(B):
+            logit_mask[b, V + offs[b]: V + offs[b + 1]] = True
+        return logit_mask
+
+    # ------------------------------------------------------------------ teacher-forced forward (padt.py:147-340), SURVEY.md §8f row 1
+    @torch.no_grad()
+    def forward_main(self, input_ids: torch.Tensor = None, attention_mask: Optional[torch.Tensor] = None, pixel_values: torch.Tensor = None,
+                     image_grid_thw: torch.Tensor = None, labels=None, output_hidden_states: bool = True, return_dict: bool = True,
+                     past_key_values=None, **unused):
+        """All-position extended logits [B, L, V + sum M] (bf16, -inf outside each row's own VRT range: padt.py:292-301) and the final-norm
+        hidden states of the prompt -- what ``PaDTSFTTrainer.compute_loss`` consumes (padt_sft_trainer.py:469-487) -- plus the four
+        ``past_*`` attributes (padt.py:322-340).  Forward only (inference engine: no autograd graph); the decode branch of forward_main
+        (``past_image_embeds`` given) is what ``generate`` runs on the device and is not exposed here.  ``hidden_states`` holds the final-norm
+        states as its only entry, so ``out.hidden_states[-1]`` is what the reference returns there."""
+        if past_key_values is not None or unused.get("past_image_embeds") is not None:
+            raise NotImplementedError("the cached decode branch of forward_main runs inside generate(); call generate() for incremental decoding")
+        if labels is not None:
+            raise NotImplementedError("the reference's labels branch views the logits as [-1, vocab_size] and fails with VRT columns (padt.py:304-316)")
+        e = self._encode(input_ids, attention_mask, pixel_values, image_grid_thw)
+        cfg = self.padt_config
+        bufs = self.engine.prefill(input_ids, e.slot, e.pos3.reshape(3, e.B * e.L), e.kv_start, e.deltas.reshape(-1).tolist(), e.offs[:-1], e.offs[1:],
+                                   e.image_embeds, e.protos, 1, [], cfg.pad_token_id, want_hidden=True)
+        hidden = bufs["prefill_hidden"]
+        logits = self.engine.extended_logits(hidden, e.protos, e.offs[:-1], e.offs[1:])
+        out = CustomGenerateDecoderOnlyOutput(
+            loss=None, logits=logits, past_key_values=None, hidden_states=(hidden,) if output_hidden_states else None, attentions=None,
+            rope_deltas=self.rope_deltas, past_image_embeds=e.protos, past_logit_mask=self._logit_mask(e.B, e.offs, e.protos.shape[0]),
+            past_high_res_image_embeds=e.high_res, past_visual_pe=e.visual_pe)
+        return out if return_dict else (logits,)
+
+    # ------------------------------------------------------------------ generate (padt.py:414-616 -> 618-800)
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor = None, attention_mask: Optional[torch.Tensor] = None, pixel_values: torch.Tensor = None,
+                 image_grid_thw: torch.Tensor = None, use_cache: bool = True, max_new_tokens: int = 20, do_sample: Optional[bool] = None,
+                 output_hidden_states: bool = False, return_dict_in_generate: bool = False, synced_gpus: bool = False,
+                 eos_token_id=None, pad_token_id=None, forced_tokens: Optional[torch.Tensor] = None, prototype_group=None,
+                 global_image_grid_thw: Optional[torch.Tensor] = None, temperature: Optional[float] = None, top_k: Optional[int] = None,
+                 top_p: Optional[float] = None, repetition_penalty: Optional[float] = None, logits_processor=None,
+                 _prefill_only: bool = False, **unused):
+        """``prototype_group`` (a torch.distributed group) switches on the sample-sharded mode (SURVEY.md §8e): this rank's
+        rows are generated exactly as in a single-process run of the LOCAL batch -- ``sequences``, ``past_image_embeds``,
+        ``past_logit_mask`` are rank-local, so the reference flow ``assign_to_local_vrt_id(seq, local_grid)`` ->
+        ``parseVRTintoCompletion`` -> ``vl_decode(feats, out.past_image_embeds, ..., local_grid, ...)`` is correct on every
+        rank -- while ONE all-gather of the prototype rows runs on a side stream.  ``out.global_view()`` waits for it and
+        returns the single-process view of the whole batch: (global table, row offset of this rank, sequences with
+        VRT ids shifted by that offset).  ``global_image_grid_thw`` [B_global,3] (rank-strided samples) lets the row counts be
+        derived from the grids, without a count collective.
+
+        Token selection (padt.py:717,740-745).  Plain greedy (no sampling, no processors: what every reference script uses,
+        utils.py:233-236) stays on the device: masked arg-max inside the decode kernel, no host round trip per token.  ``do_sample`` /
+        ``temperature`` / ``top_k`` / ``top_p`` / ``repetition_penalty`` / ``logits_processor`` (defaults from ``generation_config``,
+        as in the reference) switch to the processor path: the kernel also writes the masked bf16 logit rows, the processors and
+        ``torch.multinomial`` / ``argmax`` run on them (padt_b200/sampling.py), and the chosen ids are fed back through the
+        teacher-forcing slot of the sampler -- still without a host synchronisation per token."""
+        cfg = self.padt_config
+        gc = self.generation_config
+        pipe = LogitsPipeline(do_sample=gc.do_sample if do_sample is None else do_sample,
+                              repetition_penalty=gc.repetition_penalty if repetition_penalty is None else repetition_penalty,
+                              temperature=gc.temperature if temperature is None else temperature, top_k=gc.top_k if top_k is None else top_k,
+                              top_p=gc.top_p if top_p is None else top_p, custom=logits_processor)
+        e = self._encode(input_ids, attention_mask, pixel_values, image_grid_thw)
+        B, L = e.B, e.L
+        dev = self.device
+        image_embeds, high_res, visual_pe, protos, offs = e.image_embeds, e.high_res, e.visual_pe, e.protos, e.offs
+        exchange = None
+        if prototype_group is not None:
+            # sample-sharded inference (SURVEY.md §8e): ONE all-gather of past_image_embeds, on a side stream -- decode reads only
+            # the local rows, so the collective overlaps the local prefill + decode instead of sitting between ViT and prefill
+            import torch.distributed as dist
+            from .distributed import PrototypeExchange, rank_row_counts
+            rc = None
+            if global_image_grid_thw is not None:
+                rc = rank_row_counts(global_image_grid_thw.detach().to("cpu", torch.int64), dist.get_world_size(prototype_group),
+                                     cfg.vision.spatial_merge_size)
+            exchange = PrototypeExchange(protos, prototype_group, rc)
+        n_table = protos.shape[0]
+        V = cfg.text.vocab_size
+        eos = list(gc.eos_token_id) if eos_token_id is None else ([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id))
+        pad = gc.pad_token_id if pad_token_id is None else pad_token_id
         T = int(max_new_tokens)
+        if not pipe.is_identity and forced_tokens is not None:
+            raise ValueError("forced_tokens (teacher forcing) cannot be combined with sampling / logits processors")
         forced = None
         if forced_tokens is not None:
             forced = forced_tokens.t().contiguous()            # [B,T] -> [T,B]
-        bufs = self.engine.prefill(input_ids, slot, pos3.reshape(3, B * L), kv_start, deltas.reshape(-1).tolist(), offs[:-1], offs[1:],
-                                   image_embeds, protos, T, eos, pad, want_hidden=output_hidden_states, forced=forced)
+        elif not pipe.is_identity:
+            forced = torch.zeros((T, B), dtype=torch.int64, device=dev)     # filled one row per step by the processor path
+        bufs = self.engine.prefill(input_ids, e.slot, e.pos3.reshape(3, B * L), e.kv_start, e.deltas.reshape(-1).tolist(), offs[:-1], offs[1:],
+                                   image_embeds, protos, T, eos, pad, want_hidden=output_hidden_states, forced=forced,
+                                   want_logits=not pipe.is_identity)
         if _prefill_only:
             return None
-        # ---- decode: chunks without host sync; poll the finished flag between chunks only when EOS can stop us
-        remaining = T - 1
-        stopped_early = False
-        chunk = 32 if len(eos) > 0 else max(remaining, 1)
-        while remaining > 0:
-            n = min(chunk, remaining)
-            self.engine.decode(n, finish=False)
-            remaining -= n
-            if len(eos) > 0 and remaining > 0:
-                _, unfinished = self.engine.status()
-                if unfinished == 0:
-                    stopped_early = True
-                    break
+        if pipe.is_identity:
+            stopped_early = self._decode_greedy(T, eos)
+        else:
+            stopped_early = self._decode_with_processors(pipe, bufs, input_ids.to(dev), T, eos, pad, V + n_table)
         if not stopped_early:
             self.engine.decode(0, finish=True)
         n_sampled, _ = self.engine.status()
@@ -229,14 +292,10 @@ class PaDTForConditionalGeneration:
         if output_hidden_states:
             hs = bufs["hidden_steps"]
             hidden_states = tuple([(bufs["prefill_hidden"],)] + [(hs[k][:, None, :],) for k in range(1, t_gen)])
-        logit_mask = torch.zeros((B, V + n_table), dtype=torch.bool, device=dev)   # padt.py:196-201
-        logit_mask[:, :V] = True
-        for b in range(B):
-            logit_mask[b, V + offs[b]: V + offs[b + 1]] = True
         out = CustomGenerateDecoderOnlyOutput(
             sequences=sequences, scores=None, logits=None, attentions=None, hidden_states=hidden_states, past_key_values=None,
-            past_image_embeds=protos, past_logit_mask=logit_mask, past_high_res_image_embeds=high_res, past_visual_pe=visual_pe,
-            argmax_tokens=bufs["argmax"][:t_gen].t(),
+            past_image_embeds=protos, past_logit_mask=self._logit_mask(B, offs, n_table), past_high_res_image_embeds=high_res,
+            past_visual_pe=visual_pe, argmax_tokens=bufs["argmax"][:t_gen].t(),
         )
         if exchange is not None:
             def global_view(_ex=exchange, _seq=sequences, _V=V):
@@ -244,6 +303,43 @@ class PaDTForConditionalGeneration:
                 return table, base, torch.where(_seq >= _V, _seq + base, _seq)
             out["global_view"] = global_view
         return out if return_dict_in_generate else sequences
+
+    def _decode_greedy(self, T: int, eos) -> bool:
+        """Device-side greedy: chunks without host sync; the finished flag is polled between chunks only when EOS can stop us."""
+        remaining = T - 1
+        chunk = 32 if len(eos) > 0 else max(remaining, 1)
+        while remaining > 0:
+            n = min(chunk, remaining)
+            self.engine.decode(n, finish=False)
+            remaining -= n
+            if len(eos) > 0 and remaining > 0:
+                _, unfinished = self.engine.status()
+                if unfinished == 0:
+                    return True
+        return False
+
+    def _decode_with_processors(self, pipe: LogitsPipeline, bufs, prompt_ids: torch.Tensor, T: int, eos, pad, n_ext: int) -> bool:
+        """padt.py:713-752 around the device step: scores = logits[:, -1].float() -> processors -> multinomial / argmax -> the chosen id goes
+        into the sampler's teacher-forcing slot `forced[t]`, which the next decode launch reads when it samples token t (finished rows are
+        turned into pad ids by the device-side bookkeeping exactly as in the greedy path).  One decode launch per token, no host sync."""
+        logits, forced = bufs["logits"], bufs["forced"]
+        seq = prompt_ids
+        eos_t = torch.tensor(eos, device=seq.device) if len(eos) > 0 else None
+        unfinished = torch.ones((seq.shape[0],), dtype=torch.bool, device=seq.device)
+        for t in range(T):
+            scores = logits[:, :n_ext].float()                                    # padt.py:713 (.clone().float())
+            nxt = pipe.select(pipe.process(seq, scores))                          # padt.py:717,740-745
+            forced[t].copy_(nxt)
+            if eos_t is not None:                                                 # mirror of padt.py:748-757 for the processors' input_ids
+                nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad))
+                unfinished = unfinished & ~torch.isin(nxt, eos_t)
+            seq = torch.cat([seq, nxt[:, None]], dim=1)
+            if t == T - 1:
+                break
+            self.engine.decode(1, finish=False)                                   # samples token t (= forced[t]), runs the layers, new logits
+            if eos_t is not None and (t % 32) == 31 and not bool(unfinished.any()):
+                return True
+        return False
 
     # ------------------------------------------------------------------ vl_decode (padt.py:342-412)
     @torch.no_grad()
@@ -269,6 +365,29 @@ class PaDTForConditionalGeneration:
                 "sample_idx": samples}
 
 
+def load_generation_config(path: str, cfg: PadtConfig) -> dict:
+    """generation_config.json of a checkpoint directory -> the generate() defaults the reference's HF ``generate`` takes from it
+    (padt.py:436-447): EOS ids (Qwen2.5-VL ships [151645, 151643]: <|im_end|> AND <|endoftext|>), pad id, sampling switches, repetition
+    penalty.  Missing file / keys fall back to the PadtConfig defaults, never to config.json's single eos id."""
+    out = {"eos_token_id": None, "pad_token_id": None}
+    fn = os.path.join(path, "generation_config.json")
+    if not os.path.exists(fn):
+        return out
+    with open(fn) as f:
+        g = json.load(f)
+    eos = g.get("eos_token_id")
+    if eos is not None:
+        out["eos_token_id"] = [int(x) for x in (eos if isinstance(eos, (list, tuple)) else [eos])]
+        pad = g.get("pad_token_id")
+        out["pad_token_id"] = int(pad) if pad is not None else cfg.pad_token_id
+    elif g.get("pad_token_id") is not None:
+        out["eos_token_id"], out["pad_token_id"] = list(cfg.eos_token_ids), int(g["pad_token_id"])
+    for k in ("do_sample", "repetition_penalty", "temperature", "top_k", "top_p"):
+        if g.get(k) is not None:
+            out[k] = g[k]
+    return out
+
+
 def config_from_hf_dict(hc: dict) -> PadtConfig:
     """config.json of a PaDT checkpoint (Qwen2.5-VL layout, either flat 4.50 style or nested text_config) -> PadtConfig."""
     tc = hc.get("text_config", hc)
@@ -287,8 +406,10 @@ def config_from_hf_dict(hc: dict) -> PadtConfig:
                       tie_word_embeddings=bool(hc.get("tie_word_embeddings", tc.get("tie_word_embeddings", False))))
     decoder = DecoderConfig(hidden_size=dec.get("hidden_size", 1280), intermediate_size=dec.get("intermediate_size", 3420),
                             num_heads=dec.get("num_heads", 16), use_mask_loss=dec.get("use_mask_loss", True))
-    eos = hc.get("eos_token_id", 151645)
-    eos = tuple(eos) if isinstance(eos, (list, tuple)) else (eos,)
+    # config.json of Qwen2.5-VL carries a single eos id (<|im_end|>); the reference's generate() takes the PAIR from generation_config.json
+    # (load_generation_config).  A single id here is therefore not authoritative: keep the (151645, 151643) default unless a list is given.
+    eos = hc.get("eos_token_id")
+    eos = tuple(int(x) for x in eos) if isinstance(eos, (list, tuple)) else PadtConfig().eos_token_ids
     return PadtConfig(name=hc.get("_name_or_path", "PaDT"), vision=vision, text=text, decoder=decoder,
                       image_token_id=hc.get("image_token_id", 151655), video_token_id=hc.get("video_token_id", 151656),
                       vision_start_token_id=hc.get("vision_start_token_id", 151652), vision_end_token_id=hc.get("vision_end_token_id", 151653),
