@@ -43,6 +43,8 @@ struct VitPlan {
     int *win_off, *win_len, *full_off, *full_len;
 };
 
+#define PADT_VIT_PLAN_CACHE 16
+
 struct PadtHandle {
     PadtDims d;
     int vit_hd, dec_hd, hd;          // head dims
@@ -54,7 +56,8 @@ struct PadtHandle {
     const bf16* w_patch;
     std::vector<VitBlockW> vit;
     const bf16 *mg_ln, *mg_w0, *mg_b0, *mg_w2, *mg_b2;
-    std::map<std::string, VitPlan*> vit_plans;
+    std::map<std::string, VitPlan*> vit_plans;      // bounded LRU (PADT_VIT_PLAN_CACHE entries), keyed by the batch's grid signature
+    std::vector<std::string> vit_plan_order;        // least recently used first
     DevBuf vit_ws;
     // prototypes
     const bf16 *vn_w, *vn_b, *vp_w0, *vp_w1;

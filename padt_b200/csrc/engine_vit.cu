@@ -62,7 +62,14 @@ int get_plan(PadtHandle* h, const int64_t* grid, int n_img, VitPlan** out, cudaS
     std::string key;
     for (int i = 0; i < n_img * 3; ++i) key += std::to_string(grid[i]) + ",";
     auto it = h->vit_plans.find(key);
-    if (it != h->vit_plans.end()) { *out = it->second; return 0; }
+    if (it != h->vit_plans.end()) {
+        // most recently used key moves to the back of the LRU order
+        for (size_t i = 0; i < h->vit_plan_order.size(); ++i)
+            if (h->vit_plan_order[i] == key) { h->vit_plan_order.erase(h->vit_plan_order.begin() + i); break; }
+        h->vit_plan_order.push_back(key);
+        *out = it->second;
+        return 0;
+    }
     HostPlan hp;
     int P, M;
     build_host_plan(h->d, grid, n_img, hp, P, M);
@@ -76,8 +83,22 @@ int get_plan(PadtHandle* h, const int64_t* grid, int n_img, VitPlan** out, cudaS
     size_t o4 = put(hp.win_off), o5 = put(hp.win_len), o6 = put(hp.full_off), o7 = put(hp.full_len);
     int rc = pl->ints.ensure(packed.size() * sizeof(int));
     if (rc) { delete pl; return rc; }
-    PADT_CHECK_CUDA(cudaMemcpyAsync(pl->ints.p, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    PADT_CHECK_CUDA(cudaStreamSynchronize(st));   // `packed` is pageable host memory
+    cudaError_t ce = cudaMemcpyAsync(pl->ints.p, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);   // `packed` is pageable host memory
+    if (ce != cudaSuccess) {                                   // do not leak the half-built plan
+        pl->ints.release();
+        delete pl;
+        padt_set_error(std::string("ViT plan upload: ") + cudaGetErrorString(ce));
+        return -2;
+    }
+    // Bounded cache (an eval run over images of many sizes makes nearly every batch a new key): evict the least recently used plan.
+    // Safe here: the stream was just synchronised, so no launch in flight still reads an old plan's device tables.
+    while ((int)h->vit_plan_order.size() >= PADT_VIT_PLAN_CACHE) {
+        auto old = h->vit_plans.find(h->vit_plan_order.front());
+        if (old != h->vit_plans.end()) { old->second->ints.release(); delete old->second; h->vit_plans.erase(old); }
+        h->vit_plan_order.erase(h->vit_plan_order.begin());
+    }
+    h->vit_plan_order.push_back(key);
     int* b = pl->ints.as<int>();
     pl->embed_row_map = b + o0; pl->hpos = b + o1; pl->wpos = b + o2; pl->merge_row_map = b + o3;
     pl->win_off = b + o4; pl->win_len = b + o5; pl->full_off = b + o6; pl->full_len = b + o7;

@@ -152,3 +152,24 @@ def test_from_pretrained_synthetic_checkpoint(tmp_path, layout):
     assert torch.equal(b.sequences.cpu(), fx["sequences"]), "the loaded checkpoint reproduces the reference fixture's greedy ids"
     with pytest.raises(KeyError):
         PaDTForConditionalGeneration.from_state_dict(cfg, {k: x for k, x in sd.items() if "vis_norm" not in k})
+
+
+def test_vit_plan_cache_is_bounded_and_eviction_is_transparent():
+    """The per-grid-signature plan cache holds 16 entries (an eval run over images of many sizes makes nearly every batch a new key): after
+    more distinct grids than that, the first grid is rebuilt from scratch and must give bit-identical outputs."""
+    fx = load_golden("tiny_b1")
+    model, cfg, _ = _model(fx)
+    g = torch.Generator().manual_seed(3)
+
+    def run(h, w):
+        gg = torch.Generator().manual_seed(h * 100 + w)
+        pv = torch.randn((h * w, cfg.vision.patch_dim), generator=gg).to(torch.bfloat16).cuda()
+        return [t.clone() for t in (lambda e, hr, pe: (e, hr, pe[0], pe[1]))(*model.engine.vit_forward(pv, torch.tensor([[1, h, w]])))]
+
+    first = run(8, 12)
+    for k in range(20):                                   # 20 more signatures than the cache holds
+        run(4 + 2 * (k % 5), 4 + 2 * (k // 5) + 2 * (k % 3))
+    again = run(8, 12)
+    torch.cuda.synchronize()
+    for a, b in zip(first, again):
+        assert torch.equal(a, b)
