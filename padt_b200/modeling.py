@@ -254,6 +254,8 @@ class PaDTForConditionalGeneration:
                 rc = rank_row_counts(global_image_grid_thw.detach().to("cpu", torch.int64), dist.get_world_size(prototype_group),
                                      cfg.vision.spatial_merge_size)
             exchange = PrototypeExchange(protos, prototype_group, rc)
+            if os.environ.get("PADT_SYNC_ALLGATHER"):      # A/B switch: order the collective before the prefill, as round 1 did
+                exchange.wait()
         n_table = protos.shape[0]
         V = cfg.text.vocab_size
         eos = list(gc.eos_token_id) if eos_token_id is None else ([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id))
