@@ -128,6 +128,13 @@ int padt_op_attention(const void* q, const void* k, const void* v, void* o, int6
  * >= vocab outside [vocab + vrt_lo[b], vocab + vrt_hi[b]) of sample b become -inf.  B <= 16. */
 int padt_op_logit_mask(void* logits, int64_t ld, int rows_per_sample, int B, int vocab, int n_ext, const int32_t* vrt_lo_host,
                        const int32_t* vrt_hi_host, padt_stream_t stream);
+/* Same as padt_op_attention with the key range of every (segment, head) cut into n_split parts (split-KV, then a merge kernel): the
+ * small-q / large-kv cross attention of the PaDT decoder (padt_decoder.py:55 with 3 + n_vrt queries against 9216 image tokens).
+ * max_q_len <= 64, non-causal.  Workspaces (device, fp32): part_o [n_seg*n_heads*n_split*64*head_dim], part_ml [n_seg*n_heads*n_split*64*2]. */
+int padt_op_attention_split(const void* q, const void* k, const void* v, void* o, int64_t q_row, int64_t q_head, int64_t k_row, int64_t k_head,
+                            int64_t v_row, int64_t v_head, int64_t o_row, int64_t o_head, const int32_t* q_off, const int32_t* q_len,
+                            const int32_t* k_off, const int32_t* k_len, int n_seg, int n_heads, int max_q_len, int head_dim, float scale,
+                            int n_split, float* part_o, float* part_ml, padt_stream_t stream);
 int padt_op_rope_neox(void* x, int64_t row_stride, int n_heads, int head_dim, const float* cos, const float* sin, int cs_ld, int rows,
                       padt_stream_t stream);
 

@@ -35,7 +35,7 @@ __device__ __forceinline__ void load_tile(bf16* dst, const bf16* base, long long
     }
 }
 
-template <int HD>
+template <int HD, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS) flash_attn_kernel(AttnParams p) {
     constexpr int LD = Cfg<HD>::LD;
     constexpr int TILE = Cfg<HD>::TILE;
@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(NTHREADS) flash_attn_kernel(AttnParams p) {
     bf16* sV = sK + 2 * TILE;     // [2][TILE]
 
     // causal: later query tiles attend over more keys -> schedule them first (CTAs are issued in blockIdx order), the short ones fill the tail
-    const int seg = blockIdx.z, h = blockIdx.y, qt = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int split = SPLIT ? (int)blockIdx.x : 0;               // SPLIT: one query tile, blockIdx.x walks the key-range parts
+    const int seg = blockIdx.z, h = blockIdx.y, qt = SPLIT ? 0 : (p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x);
     const int ql = p.q_len[seg];
     if (qt * BQ >= ql) return;
     const int kl = p.k_len[seg];
@@ -65,8 +66,13 @@ __global__ void __launch_bounds__(NTHREADS) flash_attn_kernel(AttnParams p) {
         int e = qt * BQ + BQ - 1 + diag + 1;
         kv_end = e < kl ? e : kl;
     }
-    const int t_begin = ks / BKV;
-    const int t_end = (kv_end + BKV - 1) / BKV;
+    int t_begin = ks / BKV;
+    int t_end = (kv_end + BKV - 1) / BKV;
+    if (SPLIT) {
+        const int per = (t_end - t_begin + p.n_split - 1) / p.n_split;
+        t_begin += split * per;
+        t_end = t_begin + per < t_end ? t_begin + per : t_end;
+    }
 
     load_tile<HD>(sQ, qb, p.q_row, qt * BQ, ql, tid);
     if (t_begin < t_end) {
@@ -190,6 +196,19 @@ __global__ void __launch_bounds__(NTHREADS) flash_attn_kernel(AttnParams p) {
         l += __shfl_xor_sync(0xffffffffu, l, 2);
         l_run[r] = l;
     }
+    if (SPLIT) {
+        // un-normalised partial of this key-range part: rows of the single query tile
+        const size_t base = (((size_t)seg * p.n_heads + h) * p.n_split + split) * BQ;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = warp * 16 + g + r * 8;
+            float* po = p.part_o + (base + i) * HD;
+#pragma unroll
+            for (int dt = 0; dt < DT; ++dt) *reinterpret_cast<float2*>(po + dt * 8 + t4 * 2) = make_float2(o[dt][r * 2 + 0], o[dt][r * 2 + 1]);
+            if (t4 == 0) { p.part_ml[(base + i) * 2] = m_run[r]; p.part_ml[(base + i) * 2 + 1] = l_run[r]; }
+        }
+        return;
+    }
     bf16* ob = p.o + (long long)p.q_off[seg] * p.o_row + (long long)h * p.o_head;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -205,15 +224,50 @@ __global__ void __launch_bounds__(NTHREADS) flash_attn_kernel(AttnParams p) {
     }
 }
 
+// combine the key-range partials of one (segment, head): O = sum_s o_s 2^(m_s - M) / sum_s l_s 2^(m_s - M), M = max_s m_s (exp2 domain)
+template <int HD>
+__global__ void __launch_bounds__(128) attn_merge_kernel(AttnParams p) {
+    const int seg = blockIdx.y, h = blockIdx.x;
+    const int ql = p.q_len[seg];
+    const size_t base = ((size_t)seg * p.n_heads + h) * p.n_split * BQ;
+    bf16* ob = p.o + (long long)p.q_off[seg] * p.o_row + (long long)h * p.o_head;
+    for (int idx = threadIdx.x; idx < ql * (HD / 2); idx += blockDim.x) {
+        const int i = idx / (HD / 2), d = (idx % (HD / 2)) * 2;
+        float M = -INFINITY;
+        for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, p.part_ml[(base + (size_t)s * BQ + i) * 2]);
+        float L = 0.f, a = 0.f, b = 0.f;
+        for (int s = 0; s < p.n_split; ++s) {
+            const size_t row = base + (size_t)s * BQ + i;
+            const float m = p.part_ml[row * 2];
+            const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
+            L += p.part_ml[row * 2 + 1] * w;
+            const float2 v = *reinterpret_cast<const float2*>(p.part_o + row * HD + d);
+            a += v.x * w; b += v.y * w;
+        }
+        const float inv = L > 0.f ? 1.0f / L : 0.f;
+        *reinterpret_cast<uint32_t*>(ob + (long long)i * p.o_row + d) = f2_to_bf2x(a * inv, b * inv);
+    }
+}
+
 template <int HD>
 int launch_hd(const AttnParams& p, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        PADT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD>::SMEM));
+        PADT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD>::SMEM));
+        PADT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD>::SMEM));
         configured = true;
     }
+    if (p.n_split > 1) {
+        PADT_REQUIRE(p.max_q_len <= BQ && !p.causal && p.part_o && p.part_ml, "split-KV attention: one query tile, non-causal, workspaces");
+        dim3 grid(p.n_split, p.n_heads, p.n_seg);
+        flash_attn_kernel<HD, true><<<grid, NTHREADS, Cfg<HD>::SMEM, st>>>(p);
+        PADT_LAUNCH_CHECK();
+        attn_merge_kernel<HD><<<dim3(p.n_heads, p.n_seg), 128, 0, st>>>(p);
+        PADT_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid(cdiv(p.max_q_len, BQ), p.n_heads, p.n_seg);
-    flash_attn_kernel<HD><<<grid, NTHREADS, Cfg<HD>::SMEM, st>>>(p);
+    flash_attn_kernel<HD, false><<<grid, NTHREADS, Cfg<HD>::SMEM, st>>>(p);
     PADT_LAUNCH_CHECK();
     return 0;
 }

@@ -12,6 +12,8 @@ namespace {
 struct Scratch {
     bf16 *a, *b, *c, *d;   // memory-sized [NM, H]
     bf16 *qa, *qb, *qc, *qd, *qe;  // query-sized [NQ, max(H, Ipad)]
+    float *part_o, *part_ml;       // split-KV partials of the query -> image cross attention
+    int n_split;
 };
 
 struct Segs {   // device int arrays per object
@@ -22,7 +24,8 @@ struct Segs {   // device int arrays per object
 int dec_attention(PadtHandle* h, const DecAttnW& w, const bf16* q_in, int nq_rows, const bf16* k_in, const bf16* v_in, int nk_rows,
                   const int* q_off, const int* q_len, int max_q, const int* k_off, const int* k_len, int n_seg,
                   bool rope_q, bool rope_k, const float* cos, const float* sin, const int* pe_map,
-                  bf16* qbuf, bf16* kbuf, bf16* vbuf, bf16* obuf, const bf16* resid, bf16* out, cudaStream_t st) {
+                  bf16* qbuf, bf16* kbuf, bf16* vbuf, bf16* obuf, const bf16* resid, bf16* out, cudaStream_t st,
+                  int n_split = 1, float* part_o = nullptr, float* part_ml = nullptr) {
     const int H = h->d.dec_hidden, nh = h->d.dec_heads, hd = h->dec_hd;
     RC(gemm(EPI_NONE, q_in, H, w.wq, H, w.bq, nullptr, 0, qbuf, H, nullptr, nq_rows, H, H, st));
     RC(gemm(EPI_NONE, k_in, H, w.wk, H, w.bk, nullptr, 0, kbuf, H, nullptr, nk_rows, H, H, st));
@@ -35,6 +38,9 @@ int dec_attention(PadtHandle* h, const DecAttnW& w, const bf16* q_in, int nq_row
     a.q_off = q_off; a.q_len = q_len; a.k_off = k_off; a.k_len = k_len; a.k_start = nullptr;
     a.n_seg = n_seg; a.n_heads = nh; a.group = 1; a.max_q_len = max_q; a.head_dim = hd; a.causal = 0;
     a.scale = 1.0f / sqrtf((float)hd);   // flash_attn default softmax_scale (padt_decoder.py:55)
+    // a handful of queries against thousands of image tokens: one (segment, head) item is a single CTA walking the whole key range
+    // (16 CTAs for one object at 1344x1344, 66 us per call) -> cut the key range across CTAs and merge
+    if (n_split > 1 && max_q <= 64) { a.n_split = n_split; a.part_o = part_o; a.part_ml = part_ml; }
     RC(launch_attention(a, st));
     RC(gemm(EPI_RESID, obuf, H, w.wp, H, w.bp, resid, H, out, H, nullptr, nq_rows, H, H, st));
     return 0;
@@ -55,7 +61,7 @@ int dec_block(PadtHandle* h, const DecBlockW& w, bf16* query, int NQ, bf16* memo
     RC(launch_add(s.qa, query_pos, s.qb, (long long)NQ * H, st));
     RC(launch_rmsnorm(memory, H, w.norm[2], s.a, H, NM, H, eps, st));
     RC(dec_attention(h, w.q2i, s.qb, NQ, s.a, s.a, NM, sg.q_off, sg.q_len, sg.max_q, sg.m_off, sg.m_len, sg.n_obj, false, true, cos, sin,
-                     pe_map, s.qc, s.b, s.c, s.qd, query, query, st));
+                     pe_map, s.qc, s.b, s.c, s.qd, query, query, st, sg.max_m >= 256 ? s.n_split : 1, s.part_o, s.part_ml));
     // query MLP                                                                                  (:121)
     RC(launch_rmsnorm(query, H, w.norm[3], s.qa, H, NQ, H, eps, st));
     RC(gemm(EPI_GELU, s.qa, H, w.w0, H, w.b0, nullptr, 0, s.qe, Ip, nullptr, NQ, Id, H, st));
@@ -152,12 +158,18 @@ extern "C" int padt_vl_decode(PadtHandle* h, const void* vrt_feats, const int32_
     size_t o_m[4];
     for (int k = 0; k < 4; ++k) o_m[k] = take((size_t)NH * H);
     size_t o_tok = take((size_t)3 * n_obj * H), o_t0 = take((size_t)n_obj * H), o_t1 = take((size_t)n_obj * H), o_hyper = take((size_t)n_obj * (H / 16));
+    // split-KV workspaces: ~2 CTAs per SM over (objects x heads x splits), at most 16 parts
+    int n_split = (2 * h->n_sms) / (n_obj * d.dec_heads);
+    n_split = n_split < 1 ? 1 : (n_split > 16 ? 16 : n_split);
+    if (max_q > 64) n_split = 1;
+    size_t o_po = take((size_t)n_obj * d.dec_heads * n_split * 64 * hd * 2), o_pml = take((size_t)n_obj * d.dec_heads * n_split * 64 * 2 * 2);   // fp32 = 2 bf16 slots
     RC(h->dec_dws.ensure(off));
     uint8_t* base = h->dec_dws.as<uint8_t>();
     auto at = [&](size_t o) { return reinterpret_cast<bf16*>(base + o); };
     Scratch sc;
     sc.a = at(o_m[0]); sc.b = at(o_m[1]); sc.c = at(o_m[2]); sc.d = at(o_m[3]);
     sc.qa = at(o_q[0]); sc.qb = at(o_q[1]); sc.qc = at(o_q[2]); sc.qd = at(o_q[3]); sc.qe = at(o_q[4]);
+    sc.part_o = reinterpret_cast<float*>(base + o_po); sc.part_ml = reinterpret_cast<float*>(base + o_pml); sc.n_split = n_split;
     bf16 *query = at(o_query), *qpos = at(o_qpos), *low_mem = at(o_lowmem), *high_mem = at(o_highmem);
 
     // (1) VRT features -> decoder width; object queries                                          (:196-206)

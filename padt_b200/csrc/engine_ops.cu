@@ -23,6 +23,19 @@ extern "C" int padt_op_attention(const void* q, const void* k, const void* v, vo
     return launch_attention(a, (cudaStream_t)stream);
 }
 
+extern "C" int padt_op_attention_split(const void* q, const void* k, const void* v, void* o, int64_t q_row, int64_t q_head, int64_t k_row,
+                                       int64_t k_head, int64_t v_row, int64_t v_head, int64_t o_row, int64_t o_head, const int32_t* q_off,
+                                       const int32_t* q_len, const int32_t* k_off, const int32_t* k_len, int n_seg, int n_heads, int max_q_len,
+                                       int head_dim, float scale, int n_split, float* part_o, float* part_ml, padt_stream_t stream) {
+    AttnParams a = {};
+    a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.o = (bf16*)o;
+    a.q_row = q_row; a.q_head = q_head; a.k_row = k_row; a.k_head = k_head; a.v_row = v_row; a.v_head = v_head; a.o_row = o_row; a.o_head = o_head;
+    a.q_off = q_off; a.q_len = q_len; a.k_off = k_off; a.k_len = k_len; a.k_start = nullptr;
+    a.n_seg = n_seg; a.n_heads = n_heads; a.group = 1; a.max_q_len = max_q_len; a.head_dim = head_dim; a.causal = 0; a.scale = scale;
+    a.n_split = n_split; a.part_o = part_o; a.part_ml = part_ml;
+    return launch_attention(a, (cudaStream_t)stream);
+}
+
 extern "C" int padt_op_rope_neox(void* x, int64_t row_stride, int n_heads, int head_dim, const float* cos, const float* sin, int cs_ld, int rows,
                                  padt_stream_t stream) {
     return launch_rope_neox_f32((bf16*)x, row_stride, n_heads, head_dim, cos, sin, cs_ld, nullptr, rows, (cudaStream_t)stream);

@@ -149,6 +149,100 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(GemmParams p) {
     (void)n_out;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Skinny path: M <= 16 activation rows per row block (the PaDT decoder's query side: 3 + n_vrt rows per object, its heads: one row per
+// object).  The tiled kernel above launches N/64 = 20 CTAs that each walk K serially (~25 us for a 1280 x 1280 Linear whose 3.3 MB of
+// weights stream in ~1 us): 39 such launches were 1.1 ms of a 2.5 ms vl_decode (profiles/r02/call29).  Here every warp owns two weight
+// rows, the lanes stride over K in 16-byte chunks against the activation rows held in shared memory (same scheme as the decode GEMV),
+// N/16 CTAs per row block.  Same epilogue arithmetic and rounding points as gemm_bf16_kernel.
+constexpr int SK_THREADS = 256, SK_WARPS = SK_THREADS / 32, SK_MB = 16;
+
+template <int EPI>
+__global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(GemmParams p) {
+    extern __shared__ __align__(16) uint8_t sk_raw[];
+    bf16* xs = reinterpret_cast<bf16*>(sk_raw);                 // [SK_MB][Kp], Kp = K rounded up to 8, tail zeroed
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Kp = (p.K + 7) & ~7, nch = Kp >> 3;
+    const int m0 = blockIdx.y * SK_MB;
+    const int mrows = p.M - m0 < SK_MB ? p.M - m0 : SK_MB;
+    for (int i = tid; i < SK_MB * nch; i += SK_THREADS) {
+        const int r = i / nch, c = i % nch;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < mrows) {
+            v = *reinterpret_cast<const uint4*>(p.A + (size_t)(m0 + r) * p.lda + c * 8);
+            if (c * 8 + 8 > p.K) {                               // K tail: whatever sits in the pad of A must not count
+                bf16* e = reinterpret_cast<bf16*>(&v);
+                for (int k = 0; k < 8; ++k)
+                    if (c * 8 + k >= p.K) e[k] = f2bf(0.f);
+            }
+        }
+        *reinterpret_cast<uint4*>(xs + (size_t)r * Kp + c * 8) = v;
+    }
+    __syncthreads();
+    const int n_pairs = (p.N + 1) >> 1;
+    for (int pair = blockIdx.x * SK_WARPS + warp; pair < n_pairs; pair += gridDim.x * SK_WARPS) {
+        const int n0 = pair * 2, n1 = n0 + 1;
+        const bool has1 = n1 < p.N;
+        const bf16* w0 = p.W + (size_t)n0 * p.ldw;
+        const bf16* w1 = p.W + (size_t)(has1 ? n1 : n0) * p.ldw;
+        float a0[SK_MB], a1[SK_MB];
+#pragma unroll
+        for (int r = 0; r < SK_MB; ++r) { a0[r] = 0.f; a1[r] = 0.f; }
+        for (int c = lane; c < nch; c += 32) {
+            const uint4 wa = ldg_nc_v4(w0 + (size_t)c * 8), wb = ldg_nc_v4(w1 + (size_t)c * 8);
+            const float2 wa0 = bf2x_to_f2(wa.x), wa1 = bf2x_to_f2(wa.y), wa2 = bf2x_to_f2(wa.z), wa3 = bf2x_to_f2(wa.w);
+            const float2 wb0 = bf2x_to_f2(wb.x), wb1 = bf2x_to_f2(wb.y), wb2 = bf2x_to_f2(wb.z), wb3 = bf2x_to_f2(wb.w);
+#pragma unroll
+            for (int r = 0; r < SK_MB; ++r) {
+                if (r >= mrows) break;
+                const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)r * Kp + c * 8);
+                const float2 x0 = bf2x_to_f2(xv.x), x1 = bf2x_to_f2(xv.y), x2 = bf2x_to_f2(xv.z), x3 = bf2x_to_f2(xv.w);
+                float s0 = a0[r], s1 = a1[r];
+                s0 = fmaf(wa0.x, x0.x, s0); s0 = fmaf(wa0.y, x0.y, s0); s0 = fmaf(wa1.x, x1.x, s0); s0 = fmaf(wa1.y, x1.y, s0);
+                s0 = fmaf(wa2.x, x2.x, s0); s0 = fmaf(wa2.y, x2.y, s0); s0 = fmaf(wa3.x, x3.x, s0); s0 = fmaf(wa3.y, x3.y, s0);
+                s1 = fmaf(wb0.x, x0.x, s1); s1 = fmaf(wb0.y, x0.y, s1); s1 = fmaf(wb1.x, x1.x, s1); s1 = fmaf(wb1.y, x1.y, s1);
+                s1 = fmaf(wb2.x, x2.x, s1); s1 = fmaf(wb2.y, x2.y, s1); s1 = fmaf(wb3.x, x3.x, s1); s1 = fmaf(wb3.y, x3.y, s1);
+                a0[r] = s0; a1[r] = s1;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SK_MB; ++r) {
+            if (r >= mrows) break;
+            float v0 = warp_sum(a0[r]), v1 = warp_sum(a1[r]);
+            if (lane != 0) continue;
+            const int row = m0 + r;
+            if (p.bias) { v0 += bf2f(p.bias[n0]); if (has1) v1 += bf2f(p.bias[n1]); }
+            v0 = rbf(v0); v1 = rbf(v1);
+            if (EPI == EPI_GELU) { v0 = rbf(gelu_erf_f(v0)); v1 = rbf(gelu_erf_f(v1)); }
+            if (EPI == EPI_RESID) {
+                const bf16* rs = p.resid + (size_t)row * p.ldr + n0;
+                v0 = rbf(bf2f(rs[0]) + v0);
+                if (has1) v1 = rbf(bf2f(rs[1]) + v1);
+            }
+            bf16* dst = p.C + (size_t)row * p.ldc + n0;
+            dst[0] = f2bf(v0);
+            if (has1) dst[1] = f2bf(v1);
+        }
+    }
+}
+
+template <int EPI>
+int launch_skinny(const GemmParams& p, cudaStream_t st) {
+    const int Kp = (p.K + 7) & ~7;
+    const size_t smem = (size_t)SK_MB * Kp * sizeof(bf16);
+    static size_t configured = 0;
+    if (smem > configured) {
+        PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+        configured = smem > 48 * 1024 ? smem : 48 * 1024;
+    }
+    int gx = cdiv((p.N + 1) / 2, SK_WARPS);
+    gx = gx > 148 * 4 ? 148 * 4 : gx;
+    dim3 grid(gx, cdiv(p.M, SK_MB));
+    gemm_skinny_kernel<EPI><<<grid, SK_THREADS, smem, st>>>(p);
+    PADT_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int EPI>
 int launch_t(const GemmParams& p, cudaStream_t st) {
     static bool configured = false;
@@ -175,6 +269,19 @@ int launch_gemm(int epi, const GemmParams& p, cudaStream_t st) {
     PADT_REQUIRE((p.lda % 8) == 0 && (p.ldw % 8) == 0, "lda/ldw must be multiples of 8 elements (16-byte rows)");
     PADT_REQUIRE((((uintptr_t)p.A) & 15) == 0 && (((uintptr_t)p.W) & 15) == 0, "A/W must be 16-byte aligned");
     PADT_REQUIRE(((uintptr_t)p.C & 3) == 0, "C must be 4-byte aligned");
+    // few activation rows (decoder query side / heads): the skinny path; in-place residual (C == resid) is fine, every element is read
+    // and written by the same lane
+    const bool skinny_ok = p.M <= 64 && !p.out_row_map && epi != EPI_SWIGLU && (size_t)SK_MB * ((p.K + 7) & ~7) * 2 <= 200 * 1024 &&
+                           !(getenv("PADT_GEMM_SKINNY") && atoi(getenv("PADT_GEMM_SKINNY")) == 0);
+    if (skinny_ok) {
+        switch (epi) {
+            case EPI_NONE: return launch_skinny<EPI_NONE>(p, st);
+            case EPI_GELU: return launch_skinny<EPI_GELU>(p, st);
+            case EPI_RESID:
+                PADT_REQUIRE(p.resid != nullptr, "resid");
+                return launch_skinny<EPI_RESID>(p, st);
+        }
+    }
     switch (epi) {
         case EPI_NONE: return launch_t<EPI_NONE>(p, st);
         case EPI_GELU: return launch_t<EPI_GELU>(p, st);

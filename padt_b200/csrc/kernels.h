@@ -32,6 +32,11 @@ struct AttnParams {
     const int *q_off, *q_len, *k_off, *k_len, *k_start;                    // device int32 [n_seg] (k_start optional)
     int n_seg, n_heads, group, max_q_len, head_dim, causal;
     float scale;
+    // split-KV (small-q / large-kv cross attention of the PaDT decoder): n_split > 1 -> the key range of every (segment, head) is cut into
+    // n_split parts, each CTA writes an un-normalised partial (fp32 o[64][head_dim], m, l) and a merge kernel combines them.  Needs
+    // max_q_len <= 64, non-causal, and the two workspaces: part_o [n_seg*n_heads*n_split*64*head_dim], part_ml [n_seg*n_heads*n_split*64*2].
+    int n_split;
+    float *part_o, *part_ml;
 };
 int launch_attention(const AttnParams& p, cudaStream_t st);
 

@@ -208,3 +208,59 @@ def test_rope_neox_bit_exact(lib):
     _capi.check(lib.padt_op_rope_neox(xd.data_ptr(), H * hd, H, hd, cd.data_ptr(), sd.data_ptr(), hd, rows, _st()), "rope")
     torch.cuda.synchronize()
     assert torch.equal(xd.cpu(), ref), "fp32 NeoX rotary must be bit-exact (separate mul/mul/add roundings, no FMA)"
+
+
+@pytest.mark.parametrize("M,N,K,Kp", [(8, 1280, 1280, 1280), (5, 160, 256, 256), (13, 50, 212, 216), (40, 96, 3420, 3424), (1, 4, 1280, 1280)])
+def test_gemm_skinny_path_epilogues(lib, M, N, K, Kp):
+    """M <= 64 rows take the skinny (warp-per-two-weight-rows) path: bias / GELU / residual epilogues with the same rounding points as the
+    tiled kernel, K tails with padded leading dimensions, in-place residual (C == resid) as the decoder uses it."""
+    from padt_b200 import _capi
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.full((M, Kp), 7.0, device="cuda", dtype=torch.bfloat16)            # garbage in the pad of A must be ignored
+    W = torch.zeros((N, Kp), device="cuda", dtype=torch.bfloat16)
+    A[:, :K] = torch.randn((M, K), generator=g, device="cuda").to(torch.bfloat16)
+    W[:, :K] = (0.05 * torch.randn((N, K), generator=g, device="cuda")).to(torch.bfloat16)
+    b = torch.randn((N,), generator=g, device="cuda").to(torch.bfloat16)
+    R = torch.randn((M, N), generator=g, device="cuda").to(torch.bfloat16)
+    lin = (A[:, :K].float() @ W[:, :K].float().t() + b.float()).to(torch.bfloat16)
+
+    def run(epi, resid=None, out=None):
+        C = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda") if out is None else out
+        _capi.check(lib.padt_op_gemm(epi, A.data_ptr(), Kp, W.data_ptr(), Kp, b.data_ptr(), None if resid is None else resid.data_ptr(),
+                                     0 if resid is None else N, C.data_ptr(), N, None, M, N, K, _st()), "gemm")
+        torch.cuda.synchronize()
+        return C
+
+    assert_close_bf16(run(0), lin, "skinny bias", rel_to_max=0.01)
+    assert_close_bf16(run(1), torch.nn.functional.gelu(lin.float()).to(torch.bfloat16), "skinny gelu", rel_to_max=0.01)
+    assert_close_bf16(run(2, resid=R), (R.float() + lin.float()).to(torch.bfloat16), "skinny resid", rel_to_max=0.01)
+    inplace = R.clone()
+    assert_close_bf16(run(2, resid=inplace, out=inplace), (R.float() + lin.float()).to(torch.bfloat16), "skinny resid in place", rel_to_max=0.01)
+
+
+@pytest.mark.parametrize("n_split,lens", [(4, [(8, 2304)]), (16, [(8, 9216)]), (7, [(5, 700), (8, 64), (3, 1500)])])
+def test_attention_split_kv(lib, n_split, lens):
+    """Small-q / large-kv cross attention with the key range split across CTAs + merge: same result as the single-pass kernel and as the
+    oracle's FA2 restatement (head_dim 80, 2 heads), including segments whose key range has fewer tiles than parts."""
+    from padt_b200 import _capi
+    H, hd = 2, 80
+    g = torch.Generator(device="cuda").manual_seed(n_split)
+    segs_q, segs_k, qo, ko = [], [], 0, 0
+    for ql, kl in lens:
+        segs_q.append((qo, ql)); segs_k.append((ko, kl)); qo += ql; ko += kl
+    q = torch.randn((qo, H, hd), generator=g, device="cuda").to(torch.bfloat16)
+    k = torch.randn((ko, H, hd), generator=g, device="cuda").to(torch.bfloat16)
+    v = torch.randn((ko, H, hd), generator=g, device="cuda").to(torch.bfloat16)
+    single = _attention(lib, q, k, v, segs_q, segs_k, 1, False)
+    o = torch.zeros_like(q)
+    i32 = lambda xs: torch.tensor(xs, dtype=torch.int32, device="cuda")
+    qoff, qlen, koff, klen = i32([s[0] for s in segs_q]), i32([s[1] for s in segs_q]), i32([s[0] for s in segs_k]), i32([s[1] for s in segs_k])
+    n_seg = len(lens)
+    part_o = torch.empty((n_seg * H * n_split * 64 * hd,), dtype=torch.float32, device="cuda")
+    part_ml = torch.empty((n_seg * H * n_split * 64 * 2,), dtype=torch.float32, device="cuda")
+    _capi.check(lib.padt_op_attention_split(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), H * hd, hd, H * hd, hd, H * hd, hd, H * hd, hd,
+                                            qoff.data_ptr(), qlen.data_ptr(), koff.data_ptr(), klen.data_ptr(), n_seg, H, max(s[1] for s in segs_q), hd,
+                                            1.0 / math.sqrt(hd), n_split, part_o.data_ptr(), part_ml.data_ptr(), _st()), "attention_split")
+    torch.cuda.synchronize()
+    assert_close_bf16(o, single, "split-KV vs single pass", rel_to_max=0.01, cos=0.9999)
+    assert_close_bf16(o, _ref_attention(q, k, v, segs_q, segs_k, False), "split-KV vs FA2 restatement", rel_to_max=0.02)
