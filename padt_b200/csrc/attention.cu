@@ -280,6 +280,7 @@ int launch_attention(const AttnParams& p, cudaStream_t st) {
                  "attention strides must keep 16-byte alignment");
     PADT_REQUIRE(p.o_row % 2 == 0 && p.o_head % 2 == 0, "output strides must be even");
     PADT_REQUIRE(p.n_seg <= 65535 && p.n_heads <= 65535, "grid limits");
+    if (attention_tc_eligible(p, p.host_seg)) return launch_attention_tc(p, *p.host_seg, st);
     if (p.head_dim == 80) return launch_hd<80>(p, st);
     if (p.head_dim == 128) return launch_hd<128>(p, st);
     padt_set_error("launch_attention: head_dim must be 80 or 128");

@@ -41,6 +41,7 @@ struct VitPlan {
     DevBuf ints;   // all int32 tables packed
     int *embed_row_map, *hpos, *wpos, *merge_row_map;
     int *win_off, *win_len, *full_off, *full_len;
+    std::vector<int> full_off_host, full_len_host;   // host copies: the tcgen05 attention builds its tensor maps per segment
 };
 
 #define PADT_VIT_PLAN_CACHE 16

@@ -162,6 +162,8 @@ extern "C" int padt_prefill(PadtHandle* h, const int64_t* input_ids, const int32
         a.o_row = nh * hd; a.o_head = hd;
         a.q_off = segd; a.q_len = segd + B; a.k_off = segd + 2 * B; a.k_len = segd + 3 * B; a.k_start = segd + 4 * B;
         a.n_seg = B; a.n_heads = nh; a.group = nh / nkv; a.max_q_len = L; a.head_dim = hd; a.causal = 1; a.scale = scale;
+        const AttnSegHost hseg = {seg.data(), seg.data() + B, seg.data() + 2 * B, seg.data() + 3 * B};
+        a.host_seg = &hseg;
         RC(launch_attention(a, st));
         RC(gemm(EPI_RESID, attn, nh * hd, w.wo, nh * hd, nullptr, x, D, x, D, nullptr, T, D, nh * hd, st));
         RC(launch_rmsnorm(x, D, w.ln2, n, D, T, D, d.rms_eps, st));

@@ -20,6 +20,16 @@ extern "C" int padt_op_attention(const void* q, const void* k, const void* v, vo
     a.q_row = q_row; a.q_head = q_head; a.k_row = k_row; a.k_head = k_head; a.v_row = v_row; a.v_head = v_head; a.o_row = o_row; a.o_head = o_head;
     a.q_off = q_off; a.q_len = q_len; a.k_off = k_off; a.k_len = k_len; a.k_start = k_start;
     a.n_seg = n_seg; a.n_heads = n_heads; a.group = group; a.max_q_len = max_q_len; a.head_dim = head_dim; a.causal = causal; a.scale = scale;
+    // test entry: fetch the segment table so that long segments reach the tcgen05 kernel exactly as the engine's calls do
+    std::vector<int> hq(4 * (size_t)(n_seg > 0 ? n_seg : 1));
+    AttnSegHost hseg = {hq.data(), hq.data() + n_seg, hq.data() + 2 * n_seg, hq.data() + 3 * n_seg};
+    if (n_seg > 0 && n_seg <= 8 && max_q_len >= 512) {
+        const int32_t* src[4] = {q_off, q_len, k_off, k_len};
+        for (int i = 0; i < 4; ++i)
+            PADT_CHECK_CUDA(cudaMemcpyAsync(hq.data() + (size_t)i * n_seg, src[i], (size_t)n_seg * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        PADT_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        a.host_seg = &hseg;
+    }
     return launch_attention(a, (cudaStream_t)stream);
 }
 

@@ -102,6 +102,7 @@ int get_plan(PadtHandle* h, const int64_t* grid, int n_img, VitPlan** out, cudaS
     int* b = pl->ints.as<int>();
     pl->embed_row_map = b + o0; pl->hpos = b + o1; pl->wpos = b + o2; pl->merge_row_map = b + o3;
     pl->win_off = b + o4; pl->win_len = b + o5; pl->full_off = b + o6; pl->full_len = b + o7;
+    pl->full_off_host = hp.full_off; pl->full_len_host = hp.full_len;
     h->vit_plans[key] = pl;
     *out = pl;
     return 0;
@@ -176,6 +177,8 @@ extern "C" int padt_vit_forward(PadtHandle* h, const void* pixel_values, const i
         a.k_start = nullptr;
         a.n_seg = full ? pl->n_full : pl->n_win; a.n_heads = nh; a.group = 1; a.max_q_len = full ? pl->max_full : pl->max_win;
         a.head_dim = hd; a.causal = 0; a.scale = scale;
+        const AttnSegHost hseg = {pl->full_off_host.data(), pl->full_len_host.data(), pl->full_off_host.data(), pl->full_len_host.data()};
+        if (full) a.host_seg = &hseg;
         RC(launch_attention(a, st));
         RC(gemm(EPI_RESID, attn, Hv, b.wproj, Hv, b.bproj, x, Hv, x, Hv, nullptr, P, Hv, Hv, st));
         RC(launch_rmsnorm(x, Hv, b.norm2, n, Hv, P, Hv, 1e-6f, st));

@@ -37,8 +37,14 @@ struct AttnParams {
     // max_q_len <= 64, non-causal, and the two workspaces: part_o [n_seg*n_heads*n_split*64*head_dim], part_ml [n_seg*n_heads*n_split*64*2].
     int n_split;
     float *part_o, *part_ml;
+    // host copies of q_off / q_len / k_off / k_len (optional): with them the long-segment calls take the tcgen05 + TMA kernel
+    // (attention_tc.cu), whose tensor maps are built per segment on the host
+    const struct AttnSegHost* host_seg;
 };
+struct AttnSegHost { const int *q_off, *q_len, *k_off, *k_len; };
 int launch_attention(const AttnParams& p, cudaStream_t st);
+bool attention_tc_eligible(const AttnParams& p, const AttnSegHost* hs);
+int launch_attention_tc(const AttnParams& p, const AttnSegHost& hs, cudaStream_t st);
 
 // ------------------------------------------------------------------ row-wise / elementwise (elementwise.cu)
 int launch_rmsnorm(const bf16* x, int ldx, const bf16* w, bf16* y, int ldy, int rows, int dim, float eps, cudaStream_t st);

@@ -194,6 +194,57 @@ def test_attention_cross_asymmetric(lib):
     assert_close_bf16(_attention(lib, q2, k2, v2, sk, sq, 1, False), _ref_attention(q2, k2, v2, sk, sq, False), "img->q", rel_to_max=0.02)
 
 
+@pytest.mark.parametrize("hd,H,Hkv,causal,lens,starts", [
+    (80, 2, 2, False, [1500, 640], None),              # ViT full-attention shape (two images), ragged last tiles
+    (128, 4, 2, True, [700, 515], [0, 37]),            # causal GQA prefill with left pads
+    (128, 2, 1, True, [1024], None),                   # exact multiple of the tile
+    (80, 1, 1, False, [513, 512, 600, 129, 1], None),  # mixed: short segments ride along in a long-segment launch
+])
+def test_attention_long_segments_tensor_path(lib, hd, H, Hkv, causal, lens, starts):
+    """Segments >= 512 rows take the tcgen05 + TMA kernel (attention_tc.cu); same FA2 numerics as the mma.sync kernel."""
+    g = torch.Generator(device="cuda").manual_seed(hd + sum(lens))
+    segs, off = [], 0
+    for n in lens:
+        segs.append((off, n)); off += n
+    q = torch.randn((off, H, hd), generator=g, device="cuda").to(torch.bfloat16)
+    k = torch.randn((off, Hkv, hd), generator=g, device="cuda").to(torch.bfloat16)
+    v = torch.randn((off, Hkv, hd), generator=g, device="cuda").to(torch.bfloat16)
+    o = _attention(lib, q, k, v, segs, segs, H // Hkv, causal, k_start=starts)
+    ref = _ref_attention(q, k, v, segs, segs, causal, k_start=starts)
+    r = assert_close_bf16(o, ref, "long-segment attention", rel_to_max=0.02)
+    assert r["frac_exact"] > 0.5, r
+    if starts:
+        assert float(o[segs[1][0]: segs[1][0] + starts[1]].abs().max()) == 0.0
+
+
+def test_attention_kv_cache_layout_never_reads_unwritten_slots(lib):
+    """Prefill layout (engine_llm.cu): K/V live in the cache [row][kv head][s_max][d]; the slots past the prompt are not written yet.
+    Fill them with NaN: one 0 * NaN in P @ V would poison the output."""
+    from padt_b200 import _capi
+    hd, H, Hkv, B, L, s_max = 128, 4, 2, 2, 600, 704
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn((B * L, H, hd), generator=g, device="cuda").to(torch.bfloat16)
+    kc = torch.full((B, Hkv, s_max, hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    vc = torch.full((B, Hkv, s_max, hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    kc[:, :, :L] = torch.randn((B, Hkv, L, hd), generator=g, device="cuda").to(torch.bfloat16)
+    vc[:, :, :L] = torch.randn((B, Hkv, L, hd), generator=g, device="cuda").to(torch.bfloat16)
+    o = torch.zeros_like(q)
+    i32 = lambda xs: torch.tensor(xs, dtype=torch.int32, device="cuda")
+    qo, ql = i32([b * L for b in range(B)]), i32([L] * B)
+    ko, kl = i32([b * Hkv * s_max for b in range(B)]), i32([L] * B)
+    ks = i32([0, 11])
+    _capi.check(lib.padt_op_attention(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), o.data_ptr(), H * hd, hd, hd, s_max * hd, hd, s_max * hd, H * hd, hd,
+                                      qo.data_ptr(), ql.data_ptr(), ko.data_ptr(), kl.data_ptr(), ks.data_ptr(), B, H, H // Hkv, L, hd, 1,
+                                      1.0 / math.sqrt(hd), _st()), "attention")
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(o.float()).all())
+    k = kc[:, :, :L].permute(0, 2, 1, 3).reshape(B * L, Hkv, hd).contiguous()
+    v = vc[:, :, :L].permute(0, 2, 1, 3).reshape(B * L, Hkv, hd).contiguous()
+    segs = [(b * L, L) for b in range(B)]
+    ref = _ref_attention(q, k, v, segs, segs, True, k_start=[0, 11])
+    assert_close_bf16(o, ref, "kv-cache layout attention", rel_to_max=0.02)
+
+
 def test_rope_neox_bit_exact(lib):
     from padt_b200 import _capi
     import padt_oracle as O
