@@ -17,11 +17,11 @@
 
 namespace {
 
-constexpr int AT_BQ = 128, AT_BK = 128, AT_THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: softmax / correction / epilogue
+constexpr int AT_BQ = 128, AT_BK = 128, AT_THREADS = 384;   // three warpgroups: warps 0-3 / 4-7 softmax, correction, epilogue of query tile 0 / 1 (232 registers); warp 8 TMA, warp 9 MMA + TMEM owner (40 registers)
 constexpr int AT_PANEL = AT_BQ * 128;                        // one 64-column panel of a 128-row tile: 16 KB
 constexpr int AT_TILE = 2 * AT_PANEL;                        // a [128 x 128] bf16 tile = two panels
 constexpr int AT_MAXSEG = 8;
-constexpr int AT_SMEM = AT_TILE /*Q*/ + 2 * 2 * AT_TILE /*2 stages of K,V*/ + AT_TILE /*P*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+constexpr int AT_SMEM = 2 * AT_TILE /*two Q tiles*/ + 2 * 2 * AT_TILE /*2 stages of K, V*/ + 256 /*barriers*/ + 1024 /*alignment*/;
 
 struct AtMaps { CUtensorMap q[AT_MAXSEG], k[AT_MAXSEG], v[AT_MAXSEG]; };
 
@@ -34,17 +34,21 @@ __device__ __forceinline__ void at_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
 __device__ __forceinline__ void at_mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// bounded wait: a protocol error traps (the launch returns an error) instead of hanging the GPU
 __device__ __forceinline__ void at_mbar_wait(uint64_t* b, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(b)), "r"(parity)
-        : "memory");
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(b)), "r"(parity)
+            : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
 }
 __device__ __forceinline__ void at_tma_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
@@ -97,197 +101,265 @@ __device__ __forceinline__ void at_tmem_st32(uint32_t taddr, const uint32_t* r) 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void at_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void at_tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void at_tmem_st32_nowait(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+        "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ float at_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One CTA = two 128-row query tiles of one (segment, head), ping-ponged against the tensor core: while the softmax warps of tile 0 turn
+// S0(j+1) into P0(j+1) the tensor core runs P1(j) V(j) and S1(j+1), and the reverse.  TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32
+// columns each; P_t (bf16, two per column) overwrites the first 64 columns of S_t once S_t is in registers and is the TMEM A operand of
+// the P V mma.  Issue order of the mma thread: S0(0) S1(0) { PV0(j) S0(j+1) PV1(j) S1(j+1) }: tcgen05.mma executes in issue order, so
+// S_t(j+1) cannot overwrite P_t(j) before PV_t(j) has read it, and the commit after S_t(j+1) also covers PV_t(j): when the softmax
+// warps see s_ready_t they may rescale O_t.
 template <int HD>
 __global__ void __launch_bounds__(AT_THREADS, 1) flash_attn_tc_kernel(const __grid_constant__ AtMaps maps, AttnParams p) {
-    constexpr int KT = HD / 16;                 // k-steps of Q K^T (d = 80: 5; the second 64-column panel is loaded whole, one step of it is used)
+    constexpr int KT = HD / 16;                 // k-steps of Q K^T (d = 80: 5; panel 1 holds columns 64..79 + hardware zero fill)
     constexpr int OC = HD;                      // fp32 accumulator columns of O (N of the PV mma: 80 or 128, both multiples of 16)
     extern __shared__ uint8_t at_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~uintptr_t(1023));   // 128-byte swizzle atoms: 1024-byte aligned
-    uint8_t* sQ = smem;
-    uint8_t* sKV = sQ + AT_TILE;                // stage s: K at sKV + s * 2 * AT_TILE, V one tile behind it
-    uint8_t* sP = sKV + 4 * AT_TILE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + AT_TILE);
+    uint8_t* sQ = smem;                         // two query tiles
+    uint8_t* sK = sQ + 2 * AT_TILE;             // two stages
+    uint8_t* sV = sK + 2 * AT_TILE;             // two stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * AT_TILE);
     uint64_t* q_full = bars;                    // [1]
-    uint64_t* kv_full = bars + 1;               // [2]
-    uint64_t* kv_empty = bars + 3;              // [2]
-    uint64_t* s_ready = bars + 5;
-    uint64_t* p_ready = bars + 6;
-    uint64_t* pv_done = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* k_full = bars + 1;                // [2]
+    uint64_t* k_empty = bars + 3;               // [2]
+    uint64_t* v_full = bars + 5;                // [2]
+    uint64_t* v_empty = bars + 7;               // [2]
+    uint64_t* s_ready = bars + 9;               // [2] per query tile
+    uint64_t* p_ready = bars + 11;              // [2] per query tile, 128 arrivals
+    uint64_t* o_done = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int seg = blockIdx.z, h = blockIdx.y;
-    const int qt = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;   // causal: the long tiles first
+    const int qp = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;   // pair of query tiles; causal: the long ones first
     const int ql = p.q_len[seg];
-    if (qt * AT_BQ >= ql) return;                // whole CTA leaves before any barrier / TMEM use
+    if (qp * 2 * AT_BQ >= ql) return;            // whole CTA leaves before any barrier / TMEM use
     const int kl = p.k_len[seg];
     const int ks = p.k_start ? p.k_start[seg] : 0;
     const int kvh = h / p.group;
     const int diag = kl - ql;                    // causal: key j visible to query i iff j <= i + diag
     int kv_end = kl;
     if (p.causal) {
-        const int e = qt * AT_BQ + AT_BQ - 1 + diag + 1;
+        const int e = qp * 2 * AT_BQ + 2 * AT_BQ - 1 + diag + 1;
         kv_end = e < kl ? e : kl;
     }
     const int t_begin = ks / AT_BK, t_end = (kv_end + AT_BK - 1) / AT_BK;
     const int n_tiles = t_end > t_begin ? t_end - t_begin : 0;
+
     if (threadIdx.x == 0) {
         at_mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) { at_mbar_init(&kv_full[i], 1); at_mbar_init(&kv_empty[i], 1); }
-        at_mbar_init(s_ready, 1); at_mbar_init(p_ready, 128); at_mbar_init(pv_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            at_mbar_init(&k_full[i], 1); at_mbar_init(&k_empty[i], 1); at_mbar_init(&v_full[i], 1); at_mbar_init(&v_empty[i], 1);
+            at_mbar_init(&s_ready[i], 1); at_mbar_init(&p_ready[i], 128);
+        }
+        at_mbar_init(o_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.q[seg]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.k[seg]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.v[seg]) : "memory");
     }
-    if (warp == 1) {   // TMEM: 128 fp32 columns of S + up to 128 of O
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_s = *tmem_slot, tmem_o = tmem_s + 128;
+    const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {   // ---- TMA producer: Q once, then the K/V tiles through the 2-stage ring
-            at_mbar_expect_tx(q_full, AT_TILE);
-            at_tma_3d(sQ, &maps.q[seg], 0, qt * AT_BQ, h, q_full);
-            at_tma_3d(sQ + AT_PANEL, &maps.q[seg], 64, qt * AT_BQ, h, q_full);
+    // register split: the launch gives every warp 168 registers (3 warps per scheduler); 2 x 216 + 72 = 3 x 168
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      if (warp == 8) {
+        if (lane == 0 && n_tiles > 0) {   // ---- TMA producer: both query tiles once, then K and V tiles through two 2-stage rings
+            at_mbar_expect_tx(q_full, 2 * AT_TILE);
+            for (int t = 0; t < 2; ++t) {
+                at_tma_3d(sQ + t * AT_TILE, &maps.q[seg], 0, (qp * 2 + t) * AT_BQ, h, q_full);
+                at_tma_3d(sQ + t * AT_TILE + AT_PANEL, &maps.q[seg], 64, (qp * 2 + t) * AT_BQ, h, q_full);
+            }
             for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                at_mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-                at_mbar_expect_tx(&kv_full[s], 2 * AT_TILE);
-                uint8_t* sk = sKV + s * 2 * AT_TILE;
-                const int row = (t_begin + j) * AT_BK;
-                at_tma_3d(sk, &maps.k[seg], 0, row, kvh, &kv_full[s]);
-                at_tma_3d(sk + AT_PANEL, &maps.k[seg], 64, row, kvh, &kv_full[s]);
-                at_tma_3d(sk + AT_TILE, &maps.v[seg], 0, row, kvh, &kv_full[s]);
-                at_tma_3d(sk + AT_TILE + AT_PANEL, &maps.v[seg], 64, row, kvh, &kv_full[s]);
+                const int s = j & 1, row = (t_begin + j) * AT_BK;
+                const uint32_t par = ((j >> 1) & 1) ^ 1;
+                at_mbar_wait(&k_empty[s], par);
+                at_mbar_expect_tx(&k_full[s], AT_TILE);
+                at_tma_3d(sK + s * AT_TILE, &maps.k[seg], 0, row, kvh, &k_full[s]);
+                at_tma_3d(sK + s * AT_TILE + AT_PANEL, &maps.k[seg], 64, row, kvh, &k_full[s]);
+                at_mbar_wait(&v_empty[s], par);
+                at_mbar_expect_tx(&v_full[s], AT_TILE);
+                at_tma_3d(sV + s * AT_TILE, &maps.v[seg], 0, row, kvh, &v_full[s]);
+                at_tma_3d(sV + s * AT_TILE + AT_PANEL, &maps.v[seg], 64, row, kvh, &v_full[s]);
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {   // ---- MMA issuer
-            // instruction descriptors: D = f32, A = B = bf16; S: both K-major, N = 128; PV: B MN-major (bit 16), N = d
+      } else if (warp == 9) {
+        if (lane == 0 && n_tiles > 0) {   // ---- MMA issuer
+            // instruction descriptors: D = f32, A = B = bf16; S: both K-major, N = 128; PV: A from TMEM, B MN-major (bit 16), N = d
             const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
             const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(OC >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
-            at_mbar_wait(q_full, 0);
-            const uint64_t qdesc0 = at_desc_k(sQ), qdesc1 = at_desc_k(sQ + AT_PANEL);
-            const uint64_t pdesc0 = at_desc_k(sP), pdesc1 = at_desc_k(sP + AT_PANEL);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                at_mbar_wait(&kv_full[s], (j >> 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint8_t* sk = sKV + s * 2 * AT_TILE;
-                const uint64_t kdesc0 = at_desc_k(sk), kdesc1 = at_desc_k(sk + AT_PANEL);
+            auto issue_s = [&](int t, int st) {
+                const uint64_t q0 = at_desc_k(sQ + t * AT_TILE), q1 = at_desc_k(sQ + t * AT_TILE + AT_PANEL);
+                const uint64_t k0 = at_desc_k(sK + st * AT_TILE), k1 = at_desc_k(sK + st * AT_TILE + AT_PANEL);
 #pragma unroll
                 for (int k = 0; k < KT; ++k)       // 16 elements = 32 bytes inside the swizzled row: +2 in the address field; panel 1 from k = 4
-                    at_umma(tmem_s, (k < 4 ? qdesc0 : qdesc1) + 2 * (k & 3), (k < 4 ? kdesc0 : kdesc1) + 2 * (k & 3), idesc_s, k ? 1u : 0u);
-                at_commit(s_ready);
-                at_mbar_wait(p_ready, j & 1);     // P(j) is in shared memory, O is rescaled, S(j) has been read
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t vdesc = at_desc_mn(sk + AT_TILE);
+                    at_umma(tmem_base + t * 128, (k < 4 ? q0 : q1) + 2 * (k & 3), (k < 4 ? k0 : k1) + 2 * (k & 3), idesc_s, k ? 1u : 0u);
+                at_commit(&s_ready[t]);
+            };
+            auto issue_pv = [&](int t, int st, int j) {
+                const uint64_t vdesc = at_desc_mn(sV + st * AT_TILE);
 #pragma unroll
-                for (int k = 0; k < AT_BK / 16; ++k)   // 16 keys: P advances 32 bytes in its row (panel 1 from k = 4), V advances 16 rows = 2048 bytes
-                    at_umma(tmem_o, (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3), vdesc + (uint64_t)(k * 128), idesc_o, (j | k) ? 1u : 0u);
-                at_commit(&kv_empty[s]);
-                at_commit(pv_done);
+                for (int k = 0; k < AT_BK / 16; ++k)   // 16 keys: P advances 8 TMEM columns (two bf16 per column), V 16 rows = 2048 bytes
+                    at_umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8, vdesc + (uint64_t)(k * 128), idesc_o, (j | k) ? 1u : 0u);
+            };
+            at_mbar_wait(q_full, 0);
+            at_mbar_wait(&k_full[0], 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_s(0, 0);
+            issue_s(1, 0);
+            at_commit(&k_empty[0]);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j & 1, sn = s ^ 1;
+                const bool more = j + 1 < n_tiles;
+                at_mbar_wait(&v_full[s], (j >> 1) & 1);
+                at_mbar_wait(&p_ready[0], j & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue_pv(0, s, j);
+                if (more) {
+                    at_mbar_wait(&k_full[sn], ((j + 1) >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    issue_s(0, sn);
+                }
+                at_mbar_wait(&p_ready[1], j & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue_pv(1, s, j);
+                at_commit(&v_empty[s]);
+                if (more) {
+                    issue_s(1, sn);
+                    at_commit(&k_empty[sn]);
+                }
             }
+            at_commit(o_done);
         }
+      }
     } else {
-        // ---- softmax / correction / epilogue: warp w touches TMEM lanes [32 (w % 4), + 32); one thread = one query row
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        // ---- softmax / correction / epilogue: warps 0-3 own query tile 0, warps 4-7 tile 1; warp w touches TMEM lanes [32 (w % 4), + 32);
+        // one thread = one query row
+        const int t = warp >> 2;
         const int qd = warp & 3;
         const int r = qd * 32 + lane;                              // row inside the tile
-        const int i = qt * AT_BQ + r;                              // query index inside the segment
+        const int i0 = (qp * 2 + t) * AT_BQ;                       // first query row of the tile
+        const int i = i0 + r;
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        const uint32_t tmem_s = tmem_base + t * 128 + lane_addr, tmem_o = tmem_base + 256 + t * 128 + lane_addr;
         const float sl2 = p.scale * 1.4426950408889634f;
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < n_tiles; ++j) {
             const int key0 = (t_begin + j) * AT_BK;
-            at_mbar_wait(s_ready, j & 1);
+            at_mbar_wait(&s_ready[t], j & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // pass 1: row maximum of the scaled, masked scores
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int cb = 0; cb < AT_BK; cb += 32) {
-                uint32_t sv[32];
-                at_tmem_ld32(tmem_s + lane_addr + (uint32_t)cb, sv);
+            uint32_t sv[128];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int kj = key0 + cb + c;
-                    const bool ok = kj < kl && kj >= ks && (!p.causal || kj <= i + diag);
-                    mx = fmaxf(mx, ok ? __uint_as_float(sv[c]) * sl2 : -INFINITY);
+            for (int cb = 0; cb < 128; cb += 32) at_tmem_ld32_nowait(tmem_s + (uint32_t)cb, sv + cb);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // interior tiles carry no mask at all (warp-uniform test on the tile's corners)
+            const bool need_mask = key0 + AT_BK > kl || key0 < ks || (p.causal && key0 + AT_BK - 1 > i0 + diag);
+            if (need_mask) {
+                const int hi = p.causal ? (i + diag < kl - 1 ? i + diag : kl - 1) : kl - 1;   // last visible key of this row
+#pragma unroll
+                for (int c = 0; c < 128; ++c) {
+                    const int kj = key0 + c;
+                    if (kj > hi || kj < ks) sv[c] = 0xff800000u;
                 }
             }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 128; c += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(sv[c])); mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2])); mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
             const float m_new = fmaxf(m_run, mx);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
             const float alpha = exp2f(m_run - m_use);
             m_run = m_new;
-            // the previous P V must be complete before P is overwritten and O is rescaled
-            if (j > 0) {
-                at_mbar_wait(pv_done, (j - 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+            // P = exp2(s * scale*log2e - m) in fp32, row sum in fp32, P rounded to bf16 into TMEM over S (two keys per column)
+            float rs0 = 0.f, rs1 = 0.f;
+            const float neg_m = -m_use;
 #pragma unroll
-                    for (int cb = 0; cb < OC; cb += 32) {
-                        if (cb + 32 <= OC) {
-                            uint32_t ov[32];
-                            at_tmem_ld32(tmem_o + lane_addr + (uint32_t)cb, ov);
+            for (int c = 0; c < 128; c += 2) {
+                const float p0 = at_ex2(fmaf(__uint_as_float(sv[c]), sl2, neg_m));
+                const float p1 = at_ex2(fmaf(__uint_as_float(sv[c + 1]), sl2, neg_m));
+                rs0 += p0; rs1 += p1;
+                sv[c >> 1] = f2_to_bf2x(p0, p1);
+            }
+            at_tmem_st32_nowait(tmem_s, sv);
+            at_tmem_st32_nowait(tmem_s + 32u, sv + 32);
+            // (after P: the 128 score registers are dead by now)  s_ready(j) also covers P V of tile j - 1 (committed after it): O may be rescaled now
+            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
-                            at_tmem_st32(tmem_o + lane_addr + (uint32_t)cb, ov);
-                        } else {   // d = 80: the last 16 columns
-                            uint32_t ov[32];
-                            at_tmem_ld32(tmem_o + lane_addr + (uint32_t)(OC - 32), ov);   // columns 48..79: 48..63 already scaled -> scale only the upper half
+                for (int cb = 0; cb < OC; cb += 32) {
+                    uint32_t ov[32];
+                    if (cb + 32 <= OC) {
+                        at_tmem_ld32(tmem_o + (uint32_t)cb, ov);
 #pragma unroll
-                            for (int c = 16; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
-                            at_tmem_st32(tmem_o + lane_addr + (uint32_t)(OC - 32), ov);
-                        }
+                        for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
+                        at_tmem_st32_nowait(tmem_o + (uint32_t)cb, ov);
+                    } else {   // d = 80: columns 48..79, of which 48..63 are already scaled
+                        at_tmem_ld32(tmem_o + (uint32_t)(OC - 32), ov);
+#pragma unroll
+                        for (int c = 16; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
+                        at_tmem_st32_nowait(tmem_o + (uint32_t)(OC - 32), ov);
                     }
                 }
             }
-            // pass 2: P = exp2(s - m), row sum in fp32, P rounded to bf16 into the swizzled K-major A tile
-            float rs = 0.f;
-#pragma unroll 1
-            for (int cb = 0; cb < AT_BK; cb += 32) {
-                uint32_t sv[32];
-                at_tmem_ld32(tmem_s + lane_addr + (uint32_t)cb, sv);
-                uint32_t pk[16];
-#pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    const int kj = key0 + cb + c;
-                    const bool ok0 = kj < kl && kj >= ks && (!p.causal || kj <= i + diag);
-                    const bool ok1 = kj + 1 < kl && kj + 1 >= ks && (!p.causal || kj + 1 <= i + diag);
-                    const float p0 = ok0 ? exp2f(__uint_as_float(sv[c]) * sl2 - m_use) : 0.f;
-                    const float p1 = ok1 ? exp2f(__uint_as_float(sv[c + 1]) * sl2 - m_use) : 0.f;
-                    rs += p0 + p1;
-                    pk[c >> 1] = f2_to_bf2x(p0, p1);
-                }
-                uint8_t* prow = sP + (cb >> 6) * AT_PANEL + r * 128;        // panel of 64 keys, 128-byte row
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const int chunk = ((cb & 63) >> 3) + q4;                 // 16-byte chunk (8 keys) inside the row
-                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-                }
-            }
-            l_run = l_run * alpha + rs;
-            // generic-proxy writes of P -> visible to the tensor core's async proxy; TMEM loads / stores ordered before the next mma
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            at_mbar_arrive(p_ready);
+            at_mbar_arrive(&p_ready[t]);
+            l_run = l_run * alpha + (rs0 + rs1);
         }
         // ---- normalise + store
         bf16* ob = p.o + (long long)(p.q_off[seg] + i) * p.o_row + (long long)h * p.o_head;
         if (n_tiles > 0) {
-            at_mbar_wait(pv_done, (n_tiles - 1) & 1);
+            at_mbar_wait(o_done, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
 #pragma unroll
         for (int cb = 0; cb < OC; cb += 32) {
-            const int c0 = cb + 32 <= OC ? cb : OC - 32;                      // d = 80: second block re-reads columns 48..79
+            const int c0 = cb + 32 <= OC ? cb : OC - 32;                      // d = 80: the last block re-reads columns 48..79
             uint32_t ov[32];
-            if (n_tiles > 0) at_tmem_ld32(tmem_o + lane_addr + (uint32_t)c0, ov);
+            if (n_tiles > 0) at_tmem_ld32(tmem_o + (uint32_t)c0, ov);
             if (i < ql) {
 #pragma unroll
                 for (int c = (cb - c0); c < 32; c += 8) {
@@ -302,7 +374,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) flash_attn_tc_kernel(const __gr
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "n"(256) : "memory");
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -354,7 +426,7 @@ int launch_tc_hd(const AttnParams& p, const AttnSegHost& hs, cudaStream_t st) {
         rc = at_make_map(&maps.v[s], p.v + (long long)hs.k_off[s] * p.v_row, HD, hs.k_len[s], nkv, p.v_row, p.v_head);
         if (rc) return rc;
     }
-    dim3 grid(cdiv(p.max_q_len, AT_BQ), p.n_heads, p.n_seg);
+    dim3 grid(cdiv(p.max_q_len, 2 * AT_BQ), p.n_heads, p.n_seg);
     flash_attn_tc_kernel<HD><<<grid, AT_THREADS, AT_SMEM, st>>>(maps, p);
     PADT_LAUNCH_CHECK();
     return 0;
