@@ -9,6 +9,9 @@
 // Replaces the cuBLAS calls behind every nn.Linear of the reference's tensor-core-bound stages.
 #include <cuda.h>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -149,6 +152,16 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const uint32
     }
 }
 
+// Split-K of the last, partial round of tiles: `n_units` = (tiles past the full rounds) x `parts` CTAs each take 1 / parts of one
+// tile's k-blocks and write an fp32 partial to `ws`; when all parts of a tile have arrived (counter, the CTAs of a persistent grid
+// are co-resident) every part sums and finishes 1 / parts of the tile's 32-column blocks, in part order (deterministic).
+struct TcSplit {
+    int dp_tiles;             // tiles [0, dp_tiles) are walked whole (tile = cta, cta + grid, ...)
+    int n_units, parts;       // 0 units: no split
+    float* ws;                // [n_units][128][BN] fp32
+    unsigned int* counters;   // [tiles past dp_tiles][2] (arrived, finished), zero between launches
+};
+
 template <int BN>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
@@ -243,7 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS_P, 1)
-gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, GemmParams p, int tiles_m, int n_tiles) {
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, GemmParams p, int tiles_m, int n_tiles,
+                          TcSplit sp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TcSmem<BN>::STAGE);
@@ -253,6 +267,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (p.K + TC_BK - 1) / TC_BK;
+    // split-K unit of this CTA (if any): tile sp.dp_tiles + u / parts, k-blocks [kb0, kb1) of it
+    const bool has_split = (int)blockIdx.x < sp.n_units;
+    const int sk_tile = sp.dp_tiles + (has_split ? (int)blockIdx.x / sp.parts : 0), sk_part = has_split ? (int)blockIdx.x % sp.parts : 0;
+    const int sk_kb0 = (int)((long long)nk * sk_part / sp.parts), sk_kb1 = (int)((long long)nk * (sk_part + 1) / sp.parts);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(&full[i], 1); tc_mbar_init(&empty[i], 1); }
@@ -273,9 +291,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     if (warp == 0) {
         if (lane == 0) {   // ---- TMA producer: k-blocks of all of this CTA's tiles, back to back
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            auto load_range = [&](int tile, int kb_lo, int kb_hi) {
                 const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
-                for (int kb = 0; kb < nk; ++kb, ++it) {
+                for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     tc_mbar_wait(&empty[s], ((it / TC_STAGES) & 1) ^ 1);
                     tc_mbar_expect_tx(&full[s], TcSmem<BN>::STAGE);
@@ -283,18 +301,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     tma_load_2d(sa, &map_a, kb * TC_BK, m0, &full[s]);
                     tma_load_2d(sa + TcSmem<BN>::A_BYTES, &map_w, kb * TC_BK, n0, &full[s]);
                 }
-            }
+            };
+            for (int tile = blockIdx.x; tile < sp.dp_tiles; tile += gridDim.x) load_range(tile, 0, nk);
+            if (has_split) load_range(sk_tile, sk_kb0, sk_kb1);
         }
     } else if (warp == 1) {
         if (lane == 0) {   // ---- MMA issuer
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t it = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+            auto mma_range = [&](int n_kb) {
                 const uint32_t acc = ti & 1;
                 tc_mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator (first two uses pass)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < nk; ++kb, ++it) {
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     tc_mbar_wait(&full[s], (it / TC_STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -305,7 +325,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     umma_commit(&empty[s]);
                 }
                 umma_commit(&tmem_full[acc]);
-            }
+                ++ti;
+            };
+            for (int tile = blockIdx.x; tile < sp.dp_tiles; tile += gridDim.x) mma_range(nk);
+            if (has_split) mma_range(sk_kb1 - sk_kb0);
         }
     } else {
         // ---- epilogue warps: TMEM lanes [32*(warp%4), +32); lane = output row inside the tile; warps 2-5 take the first half of
@@ -313,7 +336,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         const int q = warp & 3;
         const int c_lo = warp < 6 ? 0 : BN / 2, c_hi = c_lo + BN / 2;
         uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        for (int tile = blockIdx.x; tile < sp.dp_tiles; tile += gridDim.x, ++ti) {
             const int m0 = (tile % tiles_m) * TC_BM, n0 = (tile / tiles_m) * BN;
             const uint32_t acc = ti & 1;
             tc_mbar_wait(&tmem_full[acc], (ti >> 1) & 1);
@@ -333,6 +356,71 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const int col0 = n0 + cb;
                 if (!row_ok || col0 >= p.N) continue;
                 epilogue_block<EPI>(p, r, orow, col0);
+            }
+        }
+        if (has_split) {
+            // ---- split-K unit: the fp32 partial of k-blocks [kb0, kb1) goes to this unit's workspace slot; the CTA whose arrival completes
+            // the tile sums the parts in part order (deterministic) and runs the epilogue
+            const int m0 = (sk_tile % tiles_m) * TC_BM, n0 = (sk_tile / tiles_m) * BN;
+            const uint32_t acc = ti & 1;
+            tc_mbar_wait(&tmem_full[acc], (ti >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int rt = q * 32 + lane;                              // row inside the tile
+            float* slot = sp.ws + ((size_t)blockIdx.x * TC_BM + rt) * BN;
+            for (int cb = c_lo; cb < c_hi; cb += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)cb, r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) __stcg(reinterpret_cast<uint4*>(slot + cb + j), make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps
+            unsigned int* arrive = sp.counters + 2 * (sk_tile - sp.dp_tiles);
+            if (threadIdx.x == 64) {
+                atomicAdd(arrive, 1u);
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+                } while (seen < (unsigned int)sp.parts);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            __threadfence();
+            // every part of this tile is in the workspace: this CTA finishes the 32-column blocks part, part + parts, ... for all 128 rows
+            const float* base = sp.ws + (size_t)(blockIdx.x - sk_part) * TC_BM * BN;   // part 0 of this tile
+            const int tid_e = threadIdx.x - 64;
+            const int n_blk = (BN / 32 - sk_part + sp.parts - 1) / sp.parts;
+            for (int item = tid_e; item < TC_BM * n_blk; item += 256) {
+                const int rt2 = item & (TC_BM - 1), cb = (sk_part + (item >> 7) * sp.parts) * 32;
+                const int row = m0 + rt2, col0 = n0 + cb;
+                if (row >= p.M || col0 >= p.N) continue;
+                const int orow = p.out_row_map ? p.out_row_map[row] : row;
+                const float* src = base + (size_t)rt2 * BN + cb;
+                float a[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = 0.f;
+                for (int part = 0; part < sp.parts; part += 2) {       // two parts = sixteen 16-byte loads in flight per thread
+                    const bool two = part + 1 < sp.parts;
+                    float4 v0[8], v1[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v0[j] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)part * TC_BM * BN) + j);
+                        v1[j] = two ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(part + 1) * TC_BM * BN) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {      // part order: deterministic
+                        a[4 * j] += v0[j].x; a[4 * j + 1] += v0[j].y; a[4 * j + 2] += v0[j].z; a[4 * j + 3] += v0[j].w;
+                        a[4 * j] += v1[j].x; a[4 * j + 1] += v1[j].y; a[4 * j + 2] += v1[j].z; a[4 * j + 3] += v1[j].w;
+                    }
+                }
+                uint32_t r[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(a[j]);
+                epilogue_block<EPI>(p, r, orow, col0);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+                const unsigned int old = atomicAdd(arrive + 1, 1u);
+                if (old == (unsigned int)(sp.parts - 1)) { arrive[0] = 0; arrive[1] = 0; }     // every part has read: self-cleaning for the next launch
             }
         }
     }
@@ -380,6 +468,25 @@ int sm_count() {
     return n;
 }
 
+// fp32 partial-tile workspace + per-tile arrival counters of the split-K round, one per (device, stream): launches on one stream are
+// ordered, so they can share it; the counters return to zero at the end of every launch
+int split_workspace(cudaStream_t st, float** ws, unsigned int** counters) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, void*> cache;
+    int dev = 0;
+    PADT_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    void*& buf = cache[std::make_pair(dev, st)];
+    const size_t ws_bytes = (size_t)sm_count() * TC_BM * 256 * sizeof(float), cnt_bytes = 4096;
+    if (!buf) {
+        PADT_CHECK_CUDA(cudaMalloc(&buf, ws_bytes + cnt_bytes));
+        PADT_CHECK_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(buf) + ws_bytes, 0, cnt_bytes, st));
+    }
+    *ws = static_cast<float*>(buf);
+    *counters = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(buf) + ws_bytes);
+    return 0;
+}
+
 template <int BN, int EPI>
 int launch_bn(const GemmParams& p, cudaStream_t st) {
     static bool configured = false;
@@ -396,9 +503,25 @@ int launch_bn(const GemmParams& p, cudaStream_t st) {
         dim3 grid(tiles_n, tiles_m);
         gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, st>>>(ma, mw, p);
     } else {
-        const int n_tiles = tiles_n * tiles_m;
-        const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-        gemm_tc_persistent_kernel<BN, EPI><<<grid, TC_THREADS_P, TcSmem<BN>::TOTAL, st>>>(ma, mw, p, tiles_m, n_tiles);
+        const int n_tiles = tiles_n * tiles_m, sms = sm_count();
+        const int grid = n_tiles < sms ? n_tiles : sms;
+        // tiles past the last full round: when they would occupy at most half of the SMs, split their K range so that the round fills
+        // the machine (M = 2350, N = 2048: 152 tiles on 148 SMs is two rounds for four tiles' worth of work)
+        TcSplit sp = {n_tiles, 0, 1, nullptr, nullptr};
+        static const int split_on = getenv("PADT_GEMM_SPLITK") ? atoi(getenv("PADT_GEMM_SPLITK")) : 1;
+        const int rest = n_tiles % sms, nk = (p.K + TC_BK - 1) / TC_BK;
+        if (split_on && n_tiles > sms && rest > 0 && rest * 2 <= sms && nk >= 48) {
+            int parts = sms / rest;
+            if (parts > 8) parts = 8;
+            if (parts > nk / 16) parts = nk / 16;    // a part is worth its reduction (fp32 round trip through L2, a few us) from ~16 k-blocks up
+            if (parts >= 2) {
+                float* ws = nullptr;
+                unsigned int* counters = nullptr;
+                RC_RET(split_workspace(st, &ws, &counters));
+                sp.dp_tiles = n_tiles - rest; sp.n_units = rest * parts; sp.parts = parts; sp.ws = ws; sp.counters = counters;
+            }
+        }
+        gemm_tc_persistent_kernel<BN, EPI><<<grid, TC_THREADS_P, TcSmem<BN>::TOTAL, st>>>(ma, mw, p, tiles_m, n_tiles, sp);
     }
     PADT_LAUNCH_CHECK();
     return 0;

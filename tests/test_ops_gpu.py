@@ -92,6 +92,37 @@ def test_gemm_epilogues(lib):
     assert_close_bf16(out, ref, "row map", rel_to_max=0.01)
 
 
+@pytest.mark.parametrize("M,N,K,epi", [
+    (2350, 2048, 5504, 2),     # down_proj-like: 152 tiles on 148 SMs -> the four tiles past the full round are K-split five ways
+    (2350, 2048, 11008, 2),    # llm down_proj at 3B: eight parts
+    (2350, 2560, 3072, 0),     # 42 tiles past the round, three parts each, no residual
+    (4608, 1280, 3424, 2),     # vit down-like: 180 tiles, 32 past the round, two parts (K padded to 3424, as the engine stores it)
+    (2350, 4096, 3072, 3),     # SwiGLU epilogue after the reduction
+    (2350, 2048, 2048, 2),     # K too short to split (stays whole-tile): same shape class without the split
+])
+def test_gemm_split_k_round(lib, M, N, K, epi):
+    """The persistent tcgen05 GEMM K-splits the tiles of a short last round (gemm_tc.cu TcSplit); fp32 partials are summed in part order,
+    then the usual epilogue with the HF rounding points runs.  Two launches must agree bit for bit (deterministic reduction)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K), generator=g, device="cuda").to(torch.bfloat16)
+    W = (0.03 * torch.randn((N, K), generator=g, device="cuda")).to(torch.bfloat16)
+    b = torch.randn((N,), generator=g, device="cuda").to(torch.bfloat16)
+    n_out = N // 2 if epi == 3 else N
+    R = torch.randn((M, n_out), generator=g, device="cuda").to(torch.bfloat16) if epi == 2 else None
+    lin = _ref_linear(A, W, b)
+    if epi == 2:
+        ref = (R.float() + lin.float()).to(torch.bfloat16)
+    elif epi == 3:
+        ref = (torch.nn.functional.silu(lin[:, 0::2].float()).to(torch.bfloat16).float() * lin[:, 1::2].float()).to(torch.bfloat16)
+    else:
+        ref = lin
+    C1 = _gemm(lib, epi, A, W, b, resid=R)
+    C2 = _gemm(lib, epi, A, W, b, resid=R)
+    assert torch.equal(C1, C2)
+    r = assert_close_bf16(C1, ref, f"split-k gemm {M}x{N}x{K} epi {epi}", rel_to_max=0.01)
+    assert r["frac_exact"] > 0.95, r
+
+
 def test_rmsnorm(lib):
     from padt_b200 import _capi
     import padt_oracle as O
