@@ -12,6 +12,7 @@
 #ifndef PADT_B200_H
 #define PADT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -137,6 +138,21 @@ int padt_op_attention_split(const void* q, const void* k, const void* v, void* o
                             int n_split, float* part_o, float* part_ml, padt_stream_t stream);
 int padt_op_rope_neox(void* x, int64_t row_stride, int n_heads, int head_dim, const float* cos, const float* sin, int cs_ld, int rows,
                       padt_stream_t stream);
+
+/* ---- image pre-processing on the GPU.  Replaces the host-side image-processor call of every request
+ * (eval/test_demo.py:87-93, eval/evaluation_scripts/utils.py:221-229 -> transformers 4.50 Qwen2-VL image processor: smart_resize, PIL bicubic
+ * resize on uint8, * 1/255, (x - mean) / std, patchify).  Bit-exact with Pillow's integer resampler and the float32 arithmetic of the
+ * processor; no model handle needed. */
+/* smart_resize (image_processing_qwen2_vl.py:62-88): out_hw = {resized_height, resized_width}; error when the aspect ratio exceeds 200. */
+int padt_smart_resize(int height, int width, int factor, int64_t min_pixels, int64_t max_pixels, int32_t* out_hw);
+size_t padt_preprocess_workspace_bytes(int H, int W, int out_h, int out_w);
+/* rgb: device uint8 [H, W, 3] -> pixel_values: device [(out_h / patch) * (out_w / patch), 3 * temporal * patch * patch], bf16 (out_f32 = 0:
+ * what the patch-embed GEMM consumes; equals the float32 result cast to bf16, HF:108-114) or float32 (out_f32 = 1: what the processor
+ * returns).  Rows in (h / merge, w / merge, merge, merge) order, the frame repeated `temporal` times.  workspace: device scratch of
+ * padt_preprocess_workspace_bytes. */
+int padt_preprocess_image(const uint8_t* rgb, int H, int W, int out_h, int out_w, const float* mean3_host, const float* std3_host,
+                          double rescale_factor, int patch, int temporal, int merge, void* pixel_values, int out_f32, void* workspace,
+                          size_t workspace_bytes, padt_stream_t stream);
 
 /* Host-only planning helpers of the persistent decode kernel (no device work; CPU tests): shared-memory plan
  * out4 = {slot_bytes, n_slots (always even), activation-region bytes, dynamic shared memory bytes}; stage range of one CTA for an

@@ -45,7 +45,7 @@ EXPORTED_SYMBOLS = (
     "padt_last_error", "padt_version", "padt_launch_count", "padt_weight_count", "padt_weight_name", "padt_create", "padt_destroy", "padt_set_rope_table",
     "padt_vit_plan_host", "padt_vit_forward", "padt_prototypes", "padt_prefill", "padt_decode", "padt_decode_status", "padt_set_option",
     "padt_vl_decode", "padt_op_gemm", "padt_op_rmsnorm", "padt_op_attention", "padt_op_attention_split", "padt_op_rope_neox", "padt_op_logit_mask",
-    "padt_debug_mega_plan", "padt_debug_mega_partition",
+    "padt_debug_mega_plan", "padt_debug_mega_partition", "padt_smart_resize", "padt_preprocess_workspace_bytes", "padt_preprocess_image",
 )
 
 
@@ -110,9 +110,14 @@ def load() -> C.CDLL:
     lib.padt_op_attention_split.argtypes = [C.c_void_p] * 4 + [C.c_int64] * 8 + [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                                                                                                        C.c_void_p]
     lib.padt_op_rope_neox.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.padt_smart_resize.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int32)]
+    lib.padt_preprocess_workspace_bytes.argtypes = [C.c_int] * 4
+    lib.padt_preprocess_workspace_bytes.restype = C.c_size_t
+    lib.padt_preprocess_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_double,
+                                          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("padt_last_error", "padt_version", "padt_weight_name", "padt_launch_count"):
+        if name not in ("padt_last_error", "padt_version", "padt_weight_name", "padt_launch_count", "padt_preprocess_workspace_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib
