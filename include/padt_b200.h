@@ -154,6 +154,18 @@ int padt_preprocess_image(const uint8_t* rgb, int H, int W, int out_h, int out_w
                           double rescale_factor, int patch, int temporal, int merge, void* pixel_values, int out_f32, void* workspace,
                           size_t workspace_bytes, padt_stream_t stream);
 
+/* ---- result post-processing of the batched inference harness on the GPU (eval/evaluation_scripts/utils.py:260-264).
+ * mask_logits: device bf16, one object's pred_mask plane (row stride in elements), valid region [valid_h, valid_w] = [4H, 4W].
+ * Computes F.interpolate(..., size = (out_h, out_w), mode = 'bilinear').sigmoid() > 0.5 with the reference's bf16 rounding and writes
+ *   dense_cm   device uint8 [out_w * out_h], COLUMN-major (np.asfortranarray(mask)),
+ *   run_starts device int32 [out_h * out_w] capacity: positions in the column-major flattening where the value changes (position 0 is a
+ *              start when the first pixel is 1), n_runs device int32 [1] = how many.
+ * padt_rle_string (host) turns the starts into pycocotools' compressed RLE "counts" string (maskApi.c rleToString). */
+size_t padt_mask_runs_workspace_bytes(int out_h, int out_w);
+int padt_mask_to_runs(const void* mask_logits, int64_t row_stride, int valid_h, int valid_w, int out_h, int out_w, uint8_t* dense_cm,
+                      int32_t* run_starts, int32_t* n_runs, void* workspace, size_t workspace_bytes, padt_stream_t stream);
+int padt_rle_string(const int32_t* run_starts_host, int n_starts, int total, char* out, int cap);
+
 /* Host-only planning helpers of the persistent decode kernel (no device work; CPU tests): shared-memory plan
  * out4 = {slot_bytes, n_slots (always even), activation-region bytes, dynamic shared memory bytes}; stage range of one CTA for an
  * [n_rows, K] matrix: out3 = {K segments per row group, first stage, one-past-last stage}, stage = row_group * nseg + segment. */

@@ -46,6 +46,7 @@ EXPORTED_SYMBOLS = (
     "padt_vit_plan_host", "padt_vit_forward", "padt_prototypes", "padt_prefill", "padt_decode", "padt_decode_status", "padt_set_option",
     "padt_vl_decode", "padt_op_gemm", "padt_op_rmsnorm", "padt_op_attention", "padt_op_attention_split", "padt_op_rope_neox", "padt_op_logit_mask",
     "padt_debug_mega_plan", "padt_debug_mega_partition", "padt_smart_resize", "padt_preprocess_workspace_bytes", "padt_preprocess_image",
+    "padt_mask_runs_workspace_bytes", "padt_mask_to_runs", "padt_rle_string",
 )
 
 
@@ -115,9 +116,15 @@ def load() -> C.CDLL:
     lib.padt_preprocess_workspace_bytes.restype = C.c_size_t
     lib.padt_preprocess_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_double,
                                           C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.padt_mask_runs_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    lib.padt_mask_runs_workspace_bytes.restype = C.c_size_t
+    lib.padt_mask_to_runs.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_size_t, C.c_void_p]
+    lib.padt_rle_string.argtypes = [C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_char_p, C.c_int]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("padt_last_error", "padt_version", "padt_weight_name", "padt_launch_count", "padt_preprocess_workspace_bytes"):
+        if name not in ("padt_last_error", "padt_version", "padt_weight_name", "padt_launch_count", "padt_preprocess_workspace_bytes",
+                        "padt_mask_runs_workspace_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib
