@@ -80,41 +80,82 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md recipe).  Default source: NVML in
+    this process (the library nvidia-smi itself queries) -- a polling `nvidia-smi -lms 200` child re-reads every field of the board per
+    sample and was measured to slow the 256 graph launches of a step by up to 10 % on some boxes (profiles/r02/README.md);
+    PADT_BENCH_CLOCKS=smi selects the child process."""
+
+    REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
+        self.rows = []          # [sm_mhz, sm_max_mhz, power_w, set(reasons)]
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.source = None
 
     def start(self):
+        if os.environ.get("PADT_BENCH_CLOCKS", "nvml") != "smi":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+                get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+                def poll():
+                    while not self.stop_flag.is_set():
+                        try:
+                            mask = int(get_reasons(h))
+                            self.rows.append([float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                              float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                              pynvml.nvmlDeviceGetPowerUsage(h) / 1e3, {n for n, bit in self.REASONS.items() if mask & bit}])
+                        except Exception:
+                            pass
+                        self.stop_flag.wait(0.2)
+
+                self.thread = threading.Thread(target=poll, daemon=True)
+                self.thread.start()
+                self.source = "nvml"
+                return
+            except Exception:
+                self.thread = None
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.strip().split(",")])
+            r = [x.strip() for x in line.strip().split(",")]
+            try:
+                self.rows.append([float(r[0]), float(r[1]), float(r[2]) if r[2].replace(".", "").isdigit() else None,
+                                  {n for k, n in enumerate(names) if len(r) > 3 + k and r[3 + k].lower().startswith("active")}])
+            except (ValueError, IndexError):
+                pass
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.proc is None and self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         time.sleep(0.25)
-        self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = list(self.rows)
+        sm = sorted(r[0] for r in rows)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nme in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            reasons |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": rows[0][1] if rows else None, "reasons": sorted(reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def build_prompt(cfg, L, M, seed):
@@ -241,8 +282,8 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     for w in range(max(args.warmup, 1)):
-        if rank == 0 and w == max(args.warmup, 1) - 1:
-            sampler.start()     # nvidia-smi / NVML start-up happens during the last warm-up step, its 200 ms polls cover the timed region
+        if rank == 0 and w == 0:
+            sampler.start()     # NVML start-up happens during the warm-up steps, the 200 ms polls cover the timed region
         out = gen(pv_dev, ids_dev, mask_dev)
     assert out.sequences.shape == (Bg, Lp + T)
     # --- sharded parity: this rank's sharded outputs == a single-GPU run of the same rows; the gathered table holds them at this rank's offset
