@@ -199,6 +199,33 @@ def vit_case(name, cfg, wseed, grid_hw, iseed, row_stride=16):
           f"({os.path.getsize(path) / 1024:.0f} KiB) ({time.time() - t0:.0f}s)", flush=True)
 
 
+def dec_case(name, cfg, wseed, grid_hw, objects, iseed):
+    """PaDT decoder only (D1-D4) at full image size through the UNMODIFIED vl_decode / PaDTDecoder: 9216 high-res + 2304 low-res
+    memory tokens, `objects` = VRT count per object.  Inputs come from the seed; the fixture holds the outputs and the input hash."""
+    import hashlib
+    import time
+    t0 = time.time()
+    w = random_weights(cfg, seed=wseed)
+    model, _ = build_reference(cfg, w)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import decoder_inputs          # seeded inputs shared with tests/test_model_gpu.py
+    feats, low, high, grid, pe = decoder_inputs(cfg, grid_hw, objects, iseed)
+    with torch.no_grad():
+        rd = model.vl_decode(feats, low, high, grid, pe)
+        od = O.vl_decode(w, cfg, feats, low, high, grid, pe)
+    for k in ("pred_boxes", "pred_score", "pred_mask"):
+        eq(od[k], rd[k], k)
+    sha = hashlib.sha256(b"".join(t.contiguous().view(torch.int16).numpy().tobytes() for t in [low, high] + feats[0])).hexdigest()
+    fx = dict(name=name, cfg_name=cfg.name, wseed=wseed, iseed=iseed, grid_hw=list(grid_hw), objects=list(objects), input_sha256=sha,
+              pred_boxes=rd["pred_boxes"], pred_score=rd["pred_score"], pred_mask=rd["pred_mask"], Hs=rd["pred_mask_valid_hw"][0],
+              Ws=rd["pred_mask_valid_hw"][1], sample_idx=rd["sample_idx"], oracle_mismatches=list(MISMATCHES) if MISMATCHES is not None else [])
+    path = os.path.join(GOLD, name + ".pt")
+    torch.save(fx, path)
+    print(f"[golden] {name}: decoder {grid_hw} x {objects} oracle == reference: {not fx['oracle_mismatches']}; wrote {path} "
+          f"({os.path.getsize(path) / 1024:.0f} KiB); boxes {rd['pred_boxes'].float().min():.3f}..{rd['pred_boxes'].float().max():.3f} scores "
+          f"{rd['pred_score'].float().flatten().tolist()} mask |max| {rd['pred_mask'].float().abs().max():.3f} ({time.time() - t0:.0f}s)", flush=True)
+
+
 def parser_cases(path_name="parser_cases", n_cases=200, seed=11):
     """P1/P2 cross-run: random piece streams through the UNMODIFIED reference parser / processor wrapper
     (padt_processor.py:4-151) and through padt_b200.processor; must agree; the reference's outputs are committed as JSON."""
@@ -310,6 +337,10 @@ def main():
         from padt_b200.config import padt_vit1344
         cfg = padt_vit1344()
         vit_case("vit1344", cfg, 4, (96, 96), 6)
+    # PaDT decoder at 7B dims on a 1344x1344 image (BASELINE config 4 geometry), two objects (5 and 3 VRTs).  A few minutes of CPU.
+    if "dec7b_1344" in only:
+        from padt_b200.config import padt_dec7b_1344
+        dec_case("dec7b_1344", padt_dec7b_1344(), 5, (96, 96), [5, 3], 9)
     # BASELINE.json configs[0]: PaDT_Pro_3B dims, one 336x336 image (grid 24x24, 144 image tokens), chat-template-shaped prompt
     # L = 14 + 1 + 144 + 1 + 30 = 190, 32-token greedy.  ~10 min and ~25 GB of CPU memory; opt-in.
     if "full3b_c1" in only:

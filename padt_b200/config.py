@@ -150,9 +150,25 @@ def padt_vit1344() -> PadtConfig:
     )
 
 
+def padt_dec7b_1344() -> PadtConfig:
+    """PaDT decoder at PaDT_Pro_7B dimensions (llm_hidden_state 3584, decoder 1280 / 3420 / 16 heads) over a miniature ViT / LLM: the
+    config of the 1344x1344 decoder parity fixture (BASELINE config 4 geometry; tests/golden/dec7b_1344.pt, oracle/make_golden.py)."""
+    vocab = 512
+    return PadtConfig(
+        name="PaDT_dec7b_1344",
+        vision=VisionConfig(depth=1, fullatt_block_indexes=(0,), out_hidden_size=3584),
+        text=TextConfig(hidden_size=3584, intermediate_size=1024, num_layers=1, num_heads=28, num_kv_heads=4, vocab_size=vocab,
+                        tie_word_embeddings=True),
+        decoder=DecoderConfig(),
+        image_token_id=vocab - 12, video_token_id=vocab - 11, vision_start_token_id=vocab - 14,
+        vision_end_token_id=vocab - 13, eos_token_ids=(vocab - 10,), pad_token_id=vocab - 9,
+    )
+
+
 PRESETS = {
     "PaDT_Pro_3B": padt_pro_3b,
     "PaDT_Pro_7B": padt_pro_7b,
+    "PaDT_dec7b_1344": padt_dec7b_1344,
     "PaDT_tiny": padt_tiny,
     "PaDT_small": padt_small,
     "PaDT_vit1344": padt_vit1344,

@@ -93,3 +93,16 @@ def check_tokens_margin(cand: torch.Tensor, ref: torch.Tensor, top2: torch.Tenso
             flips += 1
     report(what + " tokens", steps=T * B, exact=equal, near_tie_flips=flips, escape_ulps=ulps)
     return equal, flips
+
+
+def decoder_inputs(cfg, grid_hw, objects, iseed):
+    """Seeded inputs of a decoder-only case (shared by the generator and the test: only the outputs are stored)."""
+    g = torch.Generator().manual_seed(iseed)
+    P, D, Hd = grid_hw[0] * grid_hw[1], cfg.text.hidden_size, cfg.decoder.hidden_size
+    low = torch.randn((P // 4, D), generator=g).to(torch.bfloat16)
+    high = torch.randn((P, Hd), generator=g).to(torch.bfloat16)
+    theta = torch.rand((P, Hd // cfg.decoder.num_heads // 2), generator=g) * 6.0
+    emb = torch.cat([theta, theta], dim=-1)
+    feats = [[(2.0 * torch.randn((n, D), generator=g)).to(torch.bfloat16) for n in objects]]
+    grid = torch.tensor([[1, grid_hw[0], grid_hw[1]]], dtype=torch.long)
+    return feats, low, high, grid, (emb.cos().float(), emb.sin().float())

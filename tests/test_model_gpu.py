@@ -187,6 +187,27 @@ def test_vl_decode_alone_against_reference_golden(name):
     _check_decoder_only(dec, fx, name)
 
 
+def test_vl_decode_7b_dims_1344_against_reference_golden():
+    """D1-D4 at full image size and PaDT_Pro_7B decoder dimensions (BASELINE config 4 geometry): 9216 high-res + 2304 low-res memory tokens,
+    llm_hidden_state 3584, two objects (5 and 3 VRTs) -- the shapes that take the tcgen05 GEMM, the split-KV query->image attention and
+    the tcgen05 image->query attention.  Inputs are regenerated from the fixture's seed (hash checked); outputs come from the UNMODIFIED
+    reference (oracle == reference bit for bit when the fixture was written)."""
+    import hashlib
+    from helpers import decoder_inputs
+    from padt_b200.config import padt_dec7b_1344
+    fx = load_golden("dec7b_1344")
+    cfg = padt_dec7b_1344()
+    feats, low, high, grid, pe = decoder_inputs(cfg, tuple(fx["grid_hw"]), fx["objects"], fx["iseed"])
+    sha = hashlib.sha256(b"".join(t.contiguous().view(torch.int16).numpy().tobytes() for t in [low, high] + feats[0])).hexdigest()
+    assert sha == fx["input_sha256"], "seeded inputs differ from the ones the fixture was generated with"
+    model, _ = _model(cfg, fx["wseed"])
+    dec = model.vl_decode([[f.cuda() for f in feats[0]]], low.cuda(), high.cuda(), grid.cuda(), (pe[0].cuda(), pe[1].cuda()))
+    torch.cuda.synchronize()
+    assert dec["pred_mask"].shape == (2, 384, 384) and dec["pred_mask_valid_hw"][0].tolist() == fx["Hs"].tolist() and dec["sample_idx"] == fx["sample_idx"]
+    assert float(fx["pred_boxes"].float().max() - fx["pred_boxes"].float().min()) > 0.3, "degenerate fixture"
+    _check_decoder_only(dec, fx, "dec7b_1344")
+
+
 def test_vl_decode_empty():
     fx = load_golden("tiny_b1")
     model, _ = _model(_cfg_for(fx), fx["wseed"])
