@@ -93,6 +93,7 @@ struct PadtHandle {
     Mlp3W bbox_mlp, mask_mlp;
     const bf16 *score_w, *score_b, *up1_w, *up1_b, *up1_ln, *up2_w, *up2_b;
     DevBuf dec_dws, dec_ints;
+    std::vector<int> dec_ints_host;   // what dec_ints holds: a repeated object layout skips the upload and its stream sync
 };
 
 int engine_build_weights(PadtHandle* h);

@@ -140,9 +140,15 @@ extern "C" int padt_vl_decode(PadtHandle* h, const void* vrt_feats, const int32_
     size_t i_qoff = put(q_off), i_qlen = put(q_len), i_loff = put(l_off), i_llen = put(l_len), i_hoff = put(h_off), i_hlen = put(h_len);
     size_t i_cup = put(cu_patch), i_objw = put(obj_w), i_qsrc = put(q_src), i_tok = put(tok_rows), i_lsrc = put(low_src), i_lpe = put(low_pe),
            i_hsrc = put(high_src);
-    RC(h->dec_ints.ensure(packed.size() * sizeof(int)));
-    PADT_CHECK_CUDA(cudaMemcpyAsync(h->dec_ints.p, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    PADT_CHECK_CUDA(cudaStreamSynchronize(st));
+    // the tables depend only on (grids, object -> image map, VRT counts): the common case of an unchanged layout (a batch of requests with
+    // the same image size and object count) skips the upload and the stream sync that a copy from pageable memory implies
+    if (packed != h->dec_ints_host) {
+        h->dec_ints_host.clear();
+        RC(h->dec_ints.ensure(packed.size() * sizeof(int)));
+        PADT_CHECK_CUDA(cudaMemcpyAsync(h->dec_ints.p, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        PADT_CHECK_CUDA(cudaStreamSynchronize(st));
+        h->dec_ints_host = packed;
+    }
     const int* I = h->dec_ints.as<int>();
     // ---- workspace
     const int M_all = p_off[n_img] / unit;

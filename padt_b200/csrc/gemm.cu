@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(THREADS) gemm_bf16_kernel(GemmParams p) {
 // weights stream in ~1 us): 39 such launches were 1.1 ms of a 2.5 ms vl_decode (profiles/r02/call29).  Here every warp owns two weight
 // rows, the lanes stride over K in 16-byte chunks against the activation rows held in shared memory (same scheme as the decode GEMV),
 // N/16 CTAs per row block.  Same epilogue arithmetic and rounding points as gemm_bf16_kernel.
-constexpr int SK_THREADS = 256, SK_WARPS = SK_THREADS / 32, SK_MB = 16;
+constexpr int SK_THREADS = 256, SK_WARPS = SK_THREADS / 32, SK_MB = 16, SK_UNR = 4;
 
 template <int EPI>
 __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(GemmParams p) {
@@ -188,21 +188,35 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(GemmParams p) {
         float a0[SK_MB], a1[SK_MB];
 #pragma unroll
         for (int r = 0; r < SK_MB; ++r) { a0[r] = 0.f; a1[r] = 0.f; }
-        for (int c = lane; c < nch; c += 32) {
-            const uint4 wa = ldg_nc_v4(w0 + (size_t)c * 8), wb = ldg_nc_v4(w1 + (size_t)c * 8);
-            const float2 wa0 = bf2x_to_f2(wa.x), wa1 = bf2x_to_f2(wa.y), wa2 = bf2x_to_f2(wa.z), wa3 = bf2x_to_f2(wa.w);
-            const float2 wb0 = bf2x_to_f2(wb.x), wb1 = bf2x_to_f2(wb.y), wb2 = bf2x_to_f2(wb.z), wb3 = bf2x_to_f2(wb.w);
+        // four 16-byte chunks of both rows in flight per lane before the first FMA (K = 1280: 5 dependent round trips to HBM became 2);
+        // the accumulation order per lane is unchanged (c = lane, lane + 32, ...)
+        for (int c0 = lane; c0 < nch; c0 += 32 * SK_UNR) {
+            uint4 wav[SK_UNR], wbv[SK_UNR];
 #pragma unroll
-            for (int r = 0; r < SK_MB; ++r) {
-                if (r >= mrows) break;
-                const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)r * Kp + c * 8);
-                const float2 x0 = bf2x_to_f2(xv.x), x1 = bf2x_to_f2(xv.y), x2 = bf2x_to_f2(xv.z), x3 = bf2x_to_f2(xv.w);
-                float s0 = a0[r], s1 = a1[r];
-                s0 = fmaf(wa0.x, x0.x, s0); s0 = fmaf(wa0.y, x0.y, s0); s0 = fmaf(wa1.x, x1.x, s0); s0 = fmaf(wa1.y, x1.y, s0);
-                s0 = fmaf(wa2.x, x2.x, s0); s0 = fmaf(wa2.y, x2.y, s0); s0 = fmaf(wa3.x, x3.x, s0); s0 = fmaf(wa3.y, x3.y, s0);
-                s1 = fmaf(wb0.x, x0.x, s1); s1 = fmaf(wb0.y, x0.y, s1); s1 = fmaf(wb1.x, x1.x, s1); s1 = fmaf(wb1.y, x1.y, s1);
-                s1 = fmaf(wb2.x, x2.x, s1); s1 = fmaf(wb2.y, x2.y, s1); s1 = fmaf(wb3.x, x3.x, s1); s1 = fmaf(wb3.y, x3.y, s1);
-                a0[r] = s0; a1[r] = s1;
+            for (int u = 0; u < SK_UNR; ++u) {
+                const int c = c0 + u * 32;
+                wav[u] = c < nch ? ldg_nc_v4(w0 + (size_t)c * 8) : make_uint4(0, 0, 0, 0);
+                wbv[u] = c < nch ? ldg_nc_v4(w1 + (size_t)c * 8) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < SK_UNR; ++u) {
+                const int c = c0 + u * 32;
+                if (c >= nch) break;
+                const uint4 wa = wav[u], wb = wbv[u];
+                const float2 wa0 = bf2x_to_f2(wa.x), wa1 = bf2x_to_f2(wa.y), wa2 = bf2x_to_f2(wa.z), wa3 = bf2x_to_f2(wa.w);
+                const float2 wb0 = bf2x_to_f2(wb.x), wb1 = bf2x_to_f2(wb.y), wb2 = bf2x_to_f2(wb.z), wb3 = bf2x_to_f2(wb.w);
+#pragma unroll
+                for (int r = 0; r < SK_MB; ++r) {
+                    if (r >= mrows) break;
+                    const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)r * Kp + c * 8);
+                    const float2 x0 = bf2x_to_f2(xv.x), x1 = bf2x_to_f2(xv.y), x2 = bf2x_to_f2(xv.z), x3 = bf2x_to_f2(xv.w);
+                    float s0 = a0[r], s1 = a1[r];
+                    s0 = fmaf(wa0.x, x0.x, s0); s0 = fmaf(wa0.y, x0.y, s0); s0 = fmaf(wa1.x, x1.x, s0); s0 = fmaf(wa1.y, x1.y, s0);
+                    s0 = fmaf(wa2.x, x2.x, s0); s0 = fmaf(wa2.y, x2.y, s0); s0 = fmaf(wa3.x, x3.x, s0); s0 = fmaf(wa3.y, x3.y, s0);
+                    s1 = fmaf(wb0.x, x0.x, s1); s1 = fmaf(wb0.y, x0.y, s1); s1 = fmaf(wb1.x, x1.x, s1); s1 = fmaf(wb1.y, x1.y, s1);
+                    s1 = fmaf(wb2.x, x2.x, s1); s1 = fmaf(wb2.y, x2.y, s1); s1 = fmaf(wb3.x, x3.x, s1); s1 = fmaf(wb3.y, x3.y, s1);
+                    a0[r] = s0; a1[r] = s1;
+                }
             }
         }
 #pragma unroll
