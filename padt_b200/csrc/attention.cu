@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(128) attn_merge_kernel(AttnParams p) {
 
 template <int HD>
 int launch_hd(const AttnParams& p, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    bool& configured = configured_dev[padt_dev_slot()];
     if (!configured) {
         PADT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD>::SMEM));
         PADT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<HD>::SMEM));

@@ -411,7 +411,8 @@ int at_make_map(CUtensorMap* map, const bf16* base, int hd, long long rows, int 
 
 template <int HD>
 int launch_tc_hd(const AttnParams& p, const AttnSegHost& hs, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    bool& configured = configured_dev[padt_dev_slot()];
     if (!configured) {
         PADT_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
         configured = true;

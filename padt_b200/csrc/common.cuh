@@ -35,6 +35,13 @@ extern unsigned long long g_padt_launches;   // kernels launched by this library
     } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// index for per-device "already configured" tables: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device attribute, and one
+// process may own engines on several GPUs
+static inline int padt_dev_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+    return d;
+}
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------------

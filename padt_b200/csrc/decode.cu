@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(DecAttnArgs a) 
 template <int NB, int PRO, int EPI>
 int launch_gemv_t(const GemvArgs& a, int grid, cudaStream_t st) {
     size_t smem = (size_t)NB * a.K * sizeof(bf16);
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0};
+    size_t& configured = configured_dev[padt_dev_slot()];
     if (smem > configured) {
         PADT_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<NB, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
         configured = smem > 48 * 1024 ? smem : 48 * 1024;

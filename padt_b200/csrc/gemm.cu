@@ -244,7 +244,8 @@ template <int EPI>
 int launch_skinny(const GemmParams& p, cudaStream_t st) {
     const int Kp = (p.K + 7) & ~7;
     const size_t smem = (size_t)SK_MB * Kp * sizeof(bf16);
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {0};
+    size_t& configured = configured_dev[padt_dev_slot()];
     if (smem > configured) {
         PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
         configured = smem > 48 * 1024 ? smem : 48 * 1024;
@@ -259,7 +260,8 @@ int launch_skinny(const GemmParams& p, cudaStream_t st) {
 
 template <int EPI>
 int launch_t(const GemmParams& p, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    bool& configured = configured_dev[padt_dev_slot()];
     if (!configured) {
         PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;

@@ -489,7 +489,8 @@ int split_workspace(cudaStream_t st, float** ws, unsigned int** counters) {
 
 template <int BN, int EPI>
 int launch_bn(const GemmParams& p, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    bool& configured = configured_dev[padt_dev_slot()];
     if (!configured) {
         PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
         PADT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL));
