@@ -276,8 +276,11 @@ int launch_t(const GemmParams& p, cudaStream_t st) {
 
 int g_padt_gemm_tc = 1;
 
-int launch_gemm(int epi, const GemmParams& p, cudaStream_t st) {
-    if (p.M == 0 || p.N == 0) return 0;
+int launch_gemm(int epi, const GemmParams& p_in, cudaStream_t st) {
+    if (p_in.M == 0 || p_in.N == 0) return 0;
+    GemmParams p = p_in;
+    static const int noepi = getenv("PADT_GEMM_NOEPI") ? atoi(getenv("PADT_GEMM_NOEPI")) : 0;
+    p.dbg_skip_epilogue = noepi;
     if (const char* e = getenv("PADT_GEMM_TC")) g_padt_gemm_tc = atoi(e);   // A/B switch: 0 mma.sync, 1 persistent tcgen05, 2 one-tile tcgen05
     if (g_padt_gemm_tc && gemm_tc_eligible(p) && (epi != EPI_SWIGLU || (p.N % 2) == 0) && (epi != EPI_RESID || p.resid != nullptr))
         return launch_gemm_tc(epi, p, st);

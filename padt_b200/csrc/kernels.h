@@ -17,6 +17,7 @@ struct GemmParams {
     bf16* C; int ldc;
     const int* out_row_map;      // optional: output row = map[m] (window permutation fused into the store)
     int M, N, K;
+    int dbg_skip_epilogue;       // measurement only (PADT_GEMM_NOEPI=1): accumulators are drained but nothing is computed / stored
 };
 int launch_gemm(int epi, const GemmParams& p, cudaStream_t st);
 // tcgen05 + TMA path for the large shapes (gemm_tc.cu); launch_gemm dispatches to it when eligible and enabled
