@@ -23,6 +23,11 @@ constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
 constexpr int TC_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TC_THREADS_P = 320; // persistent kernel: warps 2-9 = epilogue (two warps per TMEM lane quarter, half of the columns each)
 
+// SiLU of the SwiGLU epilogue with the fast exponential and division (ex2.approx / rcp.approx based, a few fp32 ulps): the SwiGLU
+// epilogue is math-bound (two MUFU + ~25 instructions per pair with expf and IEEE division: 24 us of the ViT gate/up GEMM), and the
+// value is rounded to bf16 (2^-9 relative) right afterwards -- the rounding changes for about 1 element in 10^4.
+__device__ __forceinline__ float silu_fast_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
 __device__ __forceinline__ void tc_mbar_init(uint64_t* b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
@@ -124,14 +129,14 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const uint32
         uint32_t o[8];
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-            o[j >> 2] = f2_to_bf2x(rbf(silu_f(v[j])) * v[j + 1], rbf(silu_f(v[j + 2])) * v[j + 3]);
+            o[j >> 2] = f2_to_bf2x(rbf(silu_fast_f(v[j])) * v[j + 1], rbf(silu_fast_f(v[j + 2])) * v[j + 3]);
         if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
             *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
         } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 2)
-                if (col0 + j + 1 < p.N) dst[j >> 1] = f2bf(rbf(silu_f(v[j])) * v[j + 1]);
+                if (col0 + j + 1 < p.N) dst[j >> 1] = f2bf(rbf(silu_fast_f(v[j])) * v[j + 1]);
         }
     } else {
         if (EPI == EPI_GELU) {
@@ -218,7 +223,7 @@ __device__ __forceinline__ void epilogue_block_sb(const GemmParams& p, const uin
         uint32_t o[8];
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-            o[j >> 2] = f2_to_bf2x(rbf(silu_f(v[j])) * v[j + 1], rbf(silu_f(v[j + 2])) * v[j + 3]);
+            o[j >> 2] = f2_to_bf2x(rbf(silu_fast_f(v[j])) * v[j + 1], rbf(silu_fast_f(v[j + 2])) * v[j + 3]);
         if (p.dbg_skip_epilogue == 2) return;   // measurement: math without stores
         // 16 outputs = 32 contiguous bytes per row: already one whole sector per lane, no staging needed (staging made this
         // math-bound epilogue slower: more instructions per block)
@@ -230,7 +235,7 @@ __device__ __forceinline__ void epilogue_block_sb(const GemmParams& p, const uin
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2)
-                    if (col0 + j + 1 < p.N) dst[j >> 1] = f2bf(rbf(silu_f(v[j])) * v[j + 1]);
+                    if (col0 + j + 1 < p.N) dst[j >> 1] = f2bf(rbf(silu_fast_f(v[j])) * v[j + 1]);
             }
         }
         return;
