@@ -47,7 +47,7 @@ __device__ __forceinline__ void at_mbar_wait(uint64_t* b, uint32_t parity) {
             : "=r"(done)
             : "r"(smem_u32(b)), "r"(parity)
             : "memory");
-        if (spins > (1u << 24)) __trap();
+        if (spins > (1u << 28)) __trap();
     }
 }
 __device__ __forceinline__ void at_tma_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {

@@ -9,6 +9,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--lib", default="")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--no-cublas", action="store_true")
+ap.add_argument("--only", default="", help="comma-separated shape names")
 a = ap.parse_args()
 from padt_b200 import _capi
 if a.lib:
@@ -26,6 +27,8 @@ st = torch.cuda.current_stream().cuda_stream
 tot_ms = tot_cublas = tot_flop = 0.0
 rows = []
 for name, M, N, K, Kp, epi, has_bias, cnt in SHAPES:
+    if a.only and name not in a.only.split(","):
+        continue
     g = torch.Generator(device="cuda").manual_seed(1)
     A = torch.zeros((M, Kp), device="cuda", dtype=torch.bfloat16); A[:, :K] = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
     W = torch.zeros((N, Kp), device="cuda", dtype=torch.bfloat16); W[:, :K] = (0.02 * torch.randn((N, K), device="cuda", generator=g)).to(torch.bfloat16)
