@@ -222,7 +222,7 @@ def workload_config(wl, world, rows_per_gpu):
     return {"workload": wl["name"] + f" (ViT+prefill+decode), EOS disabled", "model": wl["model"], "images_per_gpu": rows_per_gpu,
             "prompt_lengths": wl["prompts"], "new_tokens": wl["new_tokens"],
             "l2_policy": "inputs > L2: every token streams > 6 GB of weights (L2 = 126 MB)",
-            "parallelism": f"dp{world} (rank-strided samples, side-stream all-gather of prototypes)" if world > 1 else "single GPU"}
+            "parallelism": f"dp{world} (rank-strided samples, rank-local outputs, no data-path collective; prototype all-gather on demand)" if world > 1 else "single GPU"}
 
 
 def run_ours(args):

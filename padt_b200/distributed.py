@@ -62,15 +62,23 @@ def global_vrt_offsets(counts_per_rank: List[List[int]]) -> List[List[int]]:
 
 
 class PrototypeExchange:
-    """The one exchange step of the sharded path, OFF the critical path: decode only ever reads the prototype rows of its own
-    samples, so the all-gather of ``past_image_embeds`` runs on a side stream while the local prefill and decode proceed; the
-    global table is only needed by callers that want the single-process view (``global_view``)."""
+    """The one exchange step of the sharded path, OFF the data path: decode only ever reads the prototype rows of its own samples
+    and every output of ``generate`` is rank-local, so the all-gather of ``past_image_embeds`` is only needed by callers that want the
+    single-process view (``global_view``).
 
-    def __init__(self, local: torch.Tensor, group=None, counts: Optional[List[int]] = None):
+    ``lazy=True`` (default of ``generate``): nothing is exchanged until ``wait()`` -- which is then a COLLECTIVE call every rank of the
+    group must make; generate itself holds no collective, ranks never wait for each other (an eager collective couples the ranks once per
+    request: a rank whose NCCL kernel waits for a late peer also holds an SM, and the cooperative decode kernel needs all of them).
+    ``lazy=False``: the all-gather is issued at construction on a side stream and overlaps the local prefill + decode."""
+
+    def __init__(self, local: torch.Tensor, group=None, counts: Optional[List[int]] = None, lazy: bool = False):
         self.local = local
+        self.group, self.counts = group, counts
         self.table = None
         self.base = 0
         self._event = None
+        if lazy:
+            return
         if local.is_cuda:
             self._stream = torch.cuda.Stream(device=local.device)
             ready = torch.cuda.Event()
@@ -85,7 +93,10 @@ class PrototypeExchange:
             self.table, self.base = allgather_prototypes(local, group, counts)
 
     def wait(self) -> Tuple[torch.Tensor, int]:
-        """Global table [sum rows, D] + this rank's row offset; orders the caller's stream after the collective."""
+        """Global table [sum rows, D] + this rank's row offset; orders the caller's stream after the collective (lazy mode: performs it
+        here, on the caller's stream -- every rank must call)."""
+        if self.table is None:
+            self.table, self.base = allgather_prototypes(self.local, self.group, self.counts)
         if self._event is not None:
             torch.cuda.current_stream(self.local.device).wait_event(self._event)
             self.table.record_stream(torch.cuda.current_stream(self.local.device))

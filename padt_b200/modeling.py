@@ -217,12 +217,13 @@ class PaDTForConditionalGeneration:
                  eos_token_id=None, pad_token_id=None, forced_tokens: Optional[torch.Tensor] = None, prototype_group=None,
                  global_image_grid_thw: Optional[torch.Tensor] = None, temperature: Optional[float] = None, top_k: Optional[int] = None,
                  top_p: Optional[float] = None, repetition_penalty: Optional[float] = None, logits_processor=None,
-                 _prefill_only: bool = False, **unused):
+                 prototype_exchange: str = "lazy", _prefill_only: bool = False, **unused):
         """``prototype_group`` (a torch.distributed group) switches on the sample-sharded mode: this rank's
         rows are generated exactly as in a single-process run of the LOCAL batch -- ``sequences``, ``past_image_embeds``,
         ``past_logit_mask`` are rank-local, so the reference flow ``assign_to_local_vrt_id(seq, local_grid)`` ->
         ``parseVRTintoCompletion`` -> ``vl_decode(feats, out.past_image_embeds, ..., local_grid, ...)`` is correct on every
-        rank -- while ONE all-gather of the prototype rows runs on a side stream.  ``out.global_view()`` waits for it and
+        rank.  ``out.global_view()`` (a collective call: every rank makes it) all-gathers the prototype rows -- or, with
+        ``prototype_exchange="eager"``, waits for the all-gather that was issued on a side stream during generate -- and
         returns the single-process view of the whole batch: (global table, row offset of this rank, sequences with
         VRT ids shifted by that offset).  ``global_image_grid_thw`` [B_global,3] (rank-strided samples) lets the row counts be
         derived from the grids, without a count collective.
@@ -245,15 +246,18 @@ class PaDTForConditionalGeneration:
         image_embeds, high_res, visual_pe, protos, offs = e.image_embeds, e.high_res, e.visual_pe, e.protos, e.offs
         exchange = None
         if prototype_group is not None:
-            # sample-sharded inference: ONE all-gather of past_image_embeds, on a side stream -- decode reads only
-            # the local rows, so the collective overlaps the local prefill + decode instead of sitting between ViT and prefill
+            # sample-sharded inference: every output is rank-local and decode reads only the local prototype rows, so
+            # generate itself holds NO collective; the ONE all-gather of past_image_embeds that rebuilds the single-process view runs when
+            # out.global_view() asks for it (a collective call).  prototype_exchange="eager": issue it now on a side stream instead, where
+            # it overlaps the local prefill + decode (couples the ranks once per request).
             import torch.distributed as dist
             from .distributed import PrototypeExchange, rank_row_counts
             rc = None
             if global_image_grid_thw is not None:
                 rc = rank_row_counts(global_image_grid_thw.detach().to("cpu", torch.int64), dist.get_world_size(prototype_group),
                                      cfg.vision.spatial_merge_size)
-            exchange = PrototypeExchange(protos, prototype_group, rc)
+            eager = prototype_exchange == "eager" or bool(os.environ.get("PADT_EAGER_ALLGATHER")) or bool(os.environ.get("PADT_SYNC_ALLGATHER"))
+            exchange = PrototypeExchange(protos, prototype_group, rc, lazy=not eager)
             if os.environ.get("PADT_SYNC_ALLGATHER"):      # A/B switch: order the collective before the prefill, as round 1 did
                 exchange.wait()
         n_table = protos.shape[0]

@@ -26,6 +26,11 @@ def _worker(rank, world, port, rows, q):
     # the same exchange with the row counts known up front (derived from the grids: no count collective), via the side-stream wrapper
     table2, base2 = PrototypeExchange(local, None, counts=list(rows)).wait()
     assert torch.equal(table, table2) and base == base2
+    # lazy mode (generate's default): nothing is exchanged at construction, wait() is the collective
+    lazy = PrototypeExchange(local, None, counts=list(rows), lazy=True)
+    assert lazy.table is None
+    table3, base3 = lazy.wait()
+    assert torch.equal(table, table3) and base == base3 and lazy.wait()[0] is table3
     q.put((rank, table, base))
     dist.barrier()
     dist.destroy_process_group()

@@ -73,6 +73,11 @@ def _worker(rank, world, port, q):
         assert torch.equal(table[base: base + single.past_image_embeds.shape[0]], single.past_image_embeds)
         L = ids.shape[1]
         assert torch.equal(seq_g[0, L:].cpu(), forced_g[0]), "global view must reproduce the batch-global ids of the fixture"
+        # the eager exchange (all-gather on a side stream during generate) gives the same view
+        eager = model.generate(**kw, prototype_group=dist.group.WORLD, global_image_grid_thw=grid_all, prototype_exchange="eager")
+        table_e, base_e, seq_e = eager.global_view()
+        torch.cuda.synchronize()
+        assert base_e == base and torch.equal(table_e, table) and torch.equal(seq_e, seq_g) and torch.equal(eager.sequences, single.sequences)
         q.put((rank, "ok", table.float().sum().item()))
     except Exception as e:     # surface the failure in the parent
         import traceback
