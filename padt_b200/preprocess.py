@@ -31,7 +31,7 @@ def smart_resize(height: int, width: int, factor: int = 28, min_pixels: int = 56
 def _to_hwc_uint8(img) -> torch.Tensor:
     """PIL image / numpy [H,W,3] / torch [H,W,3] uint8 -> contiguous torch uint8 [H,W,3] (RGB, as ``do_convert_rgb`` leaves it)."""
     if hasattr(img, "convert") and hasattr(img, "size"):          # PIL.Image without importing PIL here
-        img = np.asarray(img.convert("RGB"))
+        img = np.array(img.convert("RGB"))                        # a writable copy (torch.from_numpy warns on PIL's read-only view)
     if isinstance(img, np.ndarray):
         img = torch.from_numpy(np.ascontiguousarray(img))
     if not isinstance(img, torch.Tensor) or img.dtype != torch.uint8 or img.dim() != 3 or img.shape[-1] != 3:

@@ -186,3 +186,70 @@ def test_gpu_infer_batch_records_equal_reference_loop():
         rle = {"size": [h, w], "counts": EO.rle_to_string(EO.rle_counts(mk))}
         want.append(json.dumps({"image_id": ids[sample_idx], "score": score.item(), "category": label, "bbox": eval_box, "mask": rle}))
     assert [json.dumps(r) for r in recs] == want
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the dataset loop with a stub model
+class _StubOut(dict):
+    def __getattr__(self, k):
+        return self[k]
+
+
+class _StubModel:
+    """Stands in for PaDTForConditionalGeneration where no GPU is needed: generate returns the prompt + two text tokens, vl_decode the
+    reference's empty result (padt.py:405-412)."""
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.calls = []
+
+    def generate(self, input_ids=None, max_new_tokens=None, **kw):
+        self.calls.append(input_ids.clone())
+        seq = torch.cat([input_ids, torch.tensor([[3, 4]] * input_ids.shape[0])], dim=1)
+        hidden = tuple([(torch.zeros(input_ids.shape[0], input_ids.shape[1], 8),)] + [(torch.zeros(input_ids.shape[0], 1, 8),)])
+        return _StubOut(sequences=seq, hidden_states=hidden, past_image_embeds=None, past_high_res_image_embeds=None, past_visual_pe=None)
+
+    def vl_decode(self, feats, *a):
+        return {"pred_boxes": torch.zeros(0, 4), "pred_score": torch.zeros(0, 1), "pred_mask": torch.zeros(0, 8, 8), "pred_mask_valid_hw": (), "sample_idx": []}
+
+
+class _StubDataset:
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, sl):
+        idx = list(range(self.n))[sl]
+        return {"id": [100 + i for i in idx], "n": len(idx)}
+
+
+def test_infer_dataset_files_and_rank_striding(tmp_path):
+    """utils.py:176-266 outer loop: rank r takes batches r, r + world, ...; one completion line per sample in dataset order within the rank;
+    both files are created (and truncated) even when a rank has nothing to write; the result file stays empty without objects."""
+    from test_processor import FakeProcessor
+    from padt_b200 import VisonTextProcessingClass
+    from padt_b200.eval_harness import infer_dataset
+    V = 50
+    strings = {i: f"w{i} " for i in range(V)}
+    strings[4] = "<|im_end|>"
+    proc = VisonTextProcessingClass(FakeProcessor(V, strings))
+    proc.model_embed_token_size = V
+    ds = _StubDataset(7)
+
+    def build_inputs(batch):
+        n = batch["n"]
+        return ({"input_ids": torch.tensor([[1, 2]] * n), "attention_mask": torch.ones(n, 2, dtype=torch.long),
+                 "pixel_values": torch.zeros(4 * n, 8), "image_grid_thw": torch.tensor([[1, 2, 2]] * n)}, [(64, 48)] * n)
+
+    seen = []
+    for rank in range(2):
+        model = _StubModel()
+        f_res, f_comp = infer_dataset(model, ds, proc, build_inputs, str(tmp_path), batch_size=2, datasetname="toy", suffix="s", rank=rank, world_size=2)
+        assert os.path.basename(f_res) == f"toy_{rank}_pred_results_s.json" and os.path.basename(f_comp) == f"toy_{rank}_pred_comp_s.json"
+        lines = [json.loads(l) for l in open(f_comp)]
+        seen += [l["image_id"] for l in lines]
+        assert all(l["completion"] == "w3 " for l in lines)                 # <|im_end|> stripped (utils.py:251)
+        assert open(f_res).read() == ""
+        assert len(model.calls) == (2 if rank == 0 else 2)
+    assert sorted(seen) == [100 + i for i in range(7)]                       # every sample exactly once across the ranks

@@ -130,3 +130,26 @@ def test_gpu_preprocess_feeds_generate():
     a = model.generate(pixel_values=out["pixel_values"], **kw)
     b = model.generate(pixel_values=torch.from_numpy(want).to(torch.bfloat16).cuda(), **kw)
     assert torch.equal(a.sequences if hasattr(a, "sequences") else a, b.sequences if hasattr(b, "sequences") else b)
+
+
+def test_processor_host_side_input_handling():
+    """Host logic of GpuImageProcessor that needs no GPU: accepted image containers, RGB conversion, output sizes, argument checks."""
+    from padt_b200.preprocess import GpuImageProcessor, _to_hwc_uint8
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(2)
+    arr = rng.integers(0, 256, (30, 40, 3), dtype=np.uint8)
+    for img in (arr, torch.from_numpy(arr), Image.fromarray(arr)):
+        t = _to_hwc_uint8(img)
+        assert t.dtype == torch.uint8 and t.shape == (30, 40, 3) and torch.equal(t, torch.from_numpy(arr))
+    grey = Image.fromarray(arr[..., 0])                                   # do_convert_rgb: a grey image becomes three equal channels
+    assert torch.equal(_to_hwc_uint8(grey), torch.from_numpy(np.stack([arr[..., 0]] * 3, axis=-1)))
+    for bad in (arr.astype(np.float32), arr[..., :2], torch.zeros(3, 30, 40, dtype=torch.uint8)):
+        with pytest.raises(TypeError):
+            _to_hwc_uint8(bad)
+    p = GpuImageProcessor(device="cpu", max_pixels=28 * 28 * 1280)        # construction and size arithmetic never touch the device
+    assert p.output_size(1344, 1344) == PO.smart_resize(1344, 1344, 28, 56 * 56, 28 * 28 * 1280) == (980, 980)
+    assert GpuImageProcessor(device="cpu", max_pixels=1344 * 1344).output_size(1344, 1344) == (1344, 1344)
+    with pytest.raises(ValueError):
+        GpuImageProcessor(device="cpu", dtype=torch.float16)
+    with pytest.raises(ValueError):
+        p.output_size(10, 4000)                                           # aspect ratio > 200, like the reference
