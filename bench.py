@@ -8,9 +8,13 @@
 Default workload = BASELINE.json configs[1]: PaDT_Pro_3B random-init bf16, one synthetic 1344x1344 image per GPU (pixel_values ~ N(0,1)
 [9216,1176], grid (1,96,96)), chat-template-shaped prompt of L = 2350 tokens, 256-token greedy generate (EOS disabled so the length is
 fixed).  A "step" = one full generate (ViT + prototypes + prefill + 255 decode steps + 256 samples).  N > 1: one process per GPU, rank r
-owns image r (weak scaling); the ONE exchange step -- the all-gather of the prototype rows (past_image_embeds) -- runs on a side stream,
-overlapped with the local prefill + decode (decode only reads the local rows), and `sharded_parity` asserts that every rank's tokens and
-prototypes equal a single-GPU run of the same image.
+owns image r (weak scaling) and every output is rank-local: the timed region holds no data-path collective.  The ONE exchange step of the
+path -- the all-gather of the prototype rows (past_image_embeds) that rebuilds the single-process view -- is `out.global_view()`; the
+`sharded_parity` check (outside the timed region) calls it and asserts that every rank's tokens and prototypes equal a single-GPU run
+of the same image and that the gathered table / shifted ids equal the single-process view.
+
+Warm-up: the W requested steps, then more until the GPU has been under load for 5 s (`warmup_steps_run`); clocks / throttle reasons are
+polled every 200 ms through NVML during the timed region (`clocks`).
 
 `value`   : tokens/s with inputs already resident in HBM, CUDA events, max over ranks.
 `e2e`     : same through PaDTForConditionalGeneration.generate with pinned HOST inputs (H2D of pixel_values/ids/mask and D2H of the
