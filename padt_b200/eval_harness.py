@@ -139,6 +139,35 @@ def infer_batch(model, processor, prompt_inputs: dict, image_sizes_wh: Sequence[
     return completion_records(completions, image_ids), result_records(decoded, labels, image_sizes_wh, image_ids, encoder)
 
 
+def default_build_inputs(processor, device, open_image: Optional[Callable] = None) -> Callable:
+    """The per-batch input construction of the reference loop (utils.py:199-229) as a ``build_inputs`` callback for ``infer_dataset``:
+    chat template over ``batch['prompt']``, images opened from ``batch['image_path']`` (a list of paths per sample), images with a side
+    below 28 px up-scaled with LANCZOS keeping the aspect ratio (utils.py:204-217), processor call with left padding, tensors to
+    ``device``.  Returns (prompt_inputs, [(w, h) per image]).
+    The reference resizes inside a bare ``try / except`` with ``new_w`` / ``new_h`` only defined for small images, so a large image is
+    left alone through a NameError -- unless an earlier small image left stale values behind; here a large image is always left alone."""
+    def build(batch):
+        import PIL.Image
+        opener = open_image or PIL.Image.open
+        prompts_text = processor.apply_chat_template(batch["prompt"], tokenize=False, add_generation_prompt=True)
+        images = []
+        for sample in batch["image_path"]:
+            for path in sample:
+                img = opener(path)
+                w, h = img.size
+                if w < 28 or h < 28:
+                    if w < h:
+                        new_w, new_h = 28, int(h * (28 / w))
+                    else:
+                        new_h, new_w = 28, int(w * (28 / h))
+                    img = img.resize((new_w, new_h), PIL.Image.Resampling.LANCZOS)
+                images.append(img)
+        inputs = processor(text=prompts_text, images=images, return_tensors="pt", padding=True, padding_side="left", add_special_tokens=False)
+        inputs = {k: (v.to(device) if hasattr(v, "to") else v) for k, v in dict(inputs).items()}
+        return inputs, [im.size for im in images]
+    return build
+
+
 def shard_indices(n_items: int, batch_size: int, rank: int, world_size: int):
     """utils.py:181-182: the first index of every batch this rank takes (the total is padded up to a multiple of world_size * batch)."""
     all_number = math.ceil(n_items / (world_size * batch_size)) * world_size * batch_size
@@ -148,8 +177,8 @@ def shard_indices(n_items: int, batch_size: int, rank: int, world_size: int):
 def infer_dataset(model, dataset, processor, build_inputs: Callable, output_dir: str, batch_size: int = 1, datasetname: str = "coco", suffix: str = "",
                   rank: Optional[int] = None, world_size: Optional[int] = None, max_new_tokens: int = 1024):
     """utils.py:176-266.  ``dataset[idx: idx + batch]`` must give a dict with 'id' (list) as in the reference; ``build_inputs(batch)`` returns
-    (prompt_inputs on the device, [(w, h) per image]) -- the chat template / image loading / processor call of utils.py:199-229, which
-    needs the tokenizer files of a checkpoint and therefore stays with the caller.  Writes the two JSONL files of this rank."""
+    (prompt_inputs on the device, [(w, h) per image]) -- the chat template / image loading / processor call of utils.py:199-229;
+    ``default_build_inputs(processor, device)`` is that code for a real checkpoint's processor.  Writes the two JSONL files of this rank."""
     if rank is None or world_size is None:
         import torch.distributed as dist
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0

@@ -253,3 +253,36 @@ def test_infer_dataset_files_and_rank_striding(tmp_path):
         assert open(f_res).read() == ""
         assert len(model.calls) == (2 if rank == 0 else 2)
     assert sorted(seen) == [100 + i for i in range(7)]                       # every sample exactly once across the ranks
+
+
+def test_default_build_inputs_follows_reference_batch_construction(tmp_path):
+    """utils.py:199-229: chat template, image loading, LANCZOS up-scaling of images with a side below 28 px (aspect ratio kept), processor
+    call arguments, tensors moved to the device, PIL sizes (w, h) returned for the box / mask scaling."""
+    Image = pytest.importorskip("PIL.Image")
+    from padt_b200.eval_harness import default_build_inputs
+    paths = []
+    for i, (w, h) in enumerate([(64, 48), (20, 50), (100, 10)]):
+        p = str(tmp_path / f"im{i}.png")
+        Image.fromarray(np.full((h, w, 3), 40 * i, np.uint8)).save(p)
+        paths.append(p)
+    calls = {}
+
+    class Proc:
+        def apply_chat_template(self, prompts, tokenize, add_generation_prompt):
+            calls["template"] = (prompts, tokenize, add_generation_prompt)
+            return ["T:" + str(p) for p in prompts]
+
+        def __call__(self, **kw):
+            calls["proc"] = kw
+            n = len(kw["images"])
+            return {"input_ids": torch.ones(n, 3, dtype=torch.long), "attention_mask": torch.ones(n, 3, dtype=torch.long),
+                    "pixel_values": torch.zeros(4 * n, 8), "image_grid_thw": torch.tensor([[1, 2, 2]] * n)}
+
+    batch = {"prompt": ["p0", "p1", "p2"], "image_path": [[paths[0]], [paths[1]], [paths[2]]], "id": [1, 2, 3]}
+    inputs, sizes = default_build_inputs(Proc(), torch.device("cpu"))(batch)
+    assert calls["template"] == (["p0", "p1", "p2"], False, True)
+    kw = calls["proc"]
+    assert kw["text"] == ["T:p0", "T:p1", "T:p2"] and kw["return_tensors"] == "pt" and kw["padding"] is True and kw["padding_side"] == "left"
+    assert kw["add_special_tokens"] is False
+    assert sizes == [(64, 48), (28, int(50 * (28 / 20))), (int(100 * (28 / 10)), 28)] == [im.size for im in kw["images"]]
+    assert set(inputs) == {"input_ids", "attention_mask", "pixel_values", "image_grid_thw"} and inputs["input_ids"].device.type == "cpu"
